@@ -1,0 +1,88 @@
+// Shared host-side helpers of libecgbyte.so (status codes, error string, CUDA checks).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "ecgbyte.h"
+
+namespace ecgb {
+
+// thread-local message returned by ecgb_last_error()
+char *err_buf();
+int fail(int status, const char *fmt, ...);
+
+#define ECGB_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return ::ecgb::fail(e_ == cudaErrorMemoryAllocation ? ECGB_ENOMEM : ECGB_ECUDA,  \
+                                "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                                __FILE__, __LINE__);                                         \
+    } while (0)
+
+#define ECGB_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return ::ecgb::fail(ECGB_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+// Makes `device` current for the scope (restores the previous one).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_device(int device);  // ECGB_OK or ECGB_ENODEVICE / ECGB_EINVAL
+int sm_count(int device);
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- internal views shared between translation units ----
+
+constexpr int kNumSymbols = 26;    // len(ALPHABET), tokenizer_utils.py:12
+constexpr int kNumThresholds = 25;
+constexpr int kCells = 1024;       // uniform pre-classification cells of the quantiser
+
+// Device-resident quantiser tables.  A sample s is mapped to a cell by monotone fp32
+// arithmetic  cell = clamp(int((float(s) - lo) * scale), 0, kCells-1); each cell holds at
+// most one threshold, so symbol = qbase[cell] + (s >= thr[cell]).
+struct QuantTables {
+    float lo, scale;
+    const void *d_cell_thr;     // ThrT[kCells]  (float for f32/i16, double for f64)
+    const uint8_t *d_cell_base; // u8[kCells]
+    const void *d_thr;          // ThrT[kNumThresholds + 2] with sentinels (generic path)
+    int exact_cells;            // 1: the cell tables are usable; 0: fall back to d_thr search
+};
+
+struct VocabView {
+    const uint2 *d_nodes;   // compact nodes: x = child mask (bit c = class c), y = base << 16 | token
+    uint32_t n_nodes;
+    uint32_t smem_nodes;    // leading nodes staged in shared memory
+    const uint8_t *d_cls;   // byte -> class (0..30) or 31 = no child anywhere
+    const uint32_t *d_wide; // wide nodes (10 words each) when !compact
+    int compact;
+    int ecg_alphabet;       // class('a'+k) == k for k < 26
+};
+
+}  // namespace ecgb
+
+struct ecgb_quantizer {
+    int device;
+    ecgb_dtype dtype;
+    double p1, p99, i16_scale, lo, den;
+    double thr[ecgb::kNumThresholds];  // thresholds in the sample domain, as doubles
+    ecgb::QuantTables tab;
+    void *d_block;  // one allocation holding all tables
+};
+
+const ecgb::VocabView *ecgb_vocab_view(const ecgb_vocab *v);
+int ecgb_vocab_device(const ecgb_vocab *v);

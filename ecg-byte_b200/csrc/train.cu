@@ -1,0 +1,921 @@
+// T1-T4: byte_pair_encoding (reference: rust_bpe/src/lib.rs:58-125) on sm_100a.
+//
+// Reference loop per merge step: get_stats (full recount of overlapping pairs into a
+// hash map, lib.rs:28-48) -> argmax (lib.rs:92-94) -> merge (single-threaded in-place
+// left-to-right replacement, lib.rs:10-26).
+//
+// Here, per step, ONE streaming pass over the token stream (2-byte ids, read once,
+// written once -- the algorithmic 2*(n_t + n_{t+1}) bytes of SURVEY.md 8d):
+//   * merge_kernel: tiles of 4096 tokens, dynamic tile tickets, decoupled look-back for
+//     the output offsets; every merge site also patches the pair histogram for the
+//     windows it destroys/creates (warp-aggregated atomics into an open-addressing hash
+//     table in global memory/L2), so the histogram always equals a full recount and no
+//     second pass over the tokens is needed;
+//   * argmax_kernel: one scan of the hash table with the deterministic tie rule
+//     (max count, then smallest (left,right)); the last block to finish folds the
+//     per-block partials and records the winner on the device -- the host never
+//     synchronises inside the loop.
+// (x,x) pairs: merge() is greedy left to right, so inside a run of x only the elements
+// at even run offsets start a site (lib.rs:14-18).  A tile finds the offset of its first
+// element by scanning backwards to the start of the run that enters it.
+//
+// Sharded corpora (one trainer per rank): the same kernel takes a 2-token
+// left halo, a 3-token right halo and the parity of the x-run entering the shard; the
+// histogram patches go to a small delta table that is compacted into a list, exchanged
+// with the other ranks (all-gather, by the host) and applied by every rank, so every
+// rank holds the same global histogram and takes the same argmax without a reduction.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.h"
+
+namespace ecgb {
+
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr uint32_t kSentinel = 0xFFFFu;  // never a token id (ids <= 0xFFFE)
+constexpr int kTPB = 256;                // threads per block of the merge kernel
+constexpr int kIPT = 16;                 // tokens per thread
+constexpr int kTile = kTPB * kIPT;
+constexpr int kBoundaryWords = 16;       // u32 words of boundary info per rank
+constexpr int kArgmaxBlocks = 592;       // 148 SMs x 4
+
+struct PairTable {
+    uint32_t *keys;            // left << 16 | right, kEmptyKey = free
+    unsigned long long *cnt;   // two's-complement adds; always >= 0 between steps
+    uint32_t mask;             // capacity - 1
+    uint32_t *used;            // slots claimed
+    uint32_t *overflow;        // set when a probe sequence wrapped
+};
+
+struct Best {
+    unsigned long long count;  // 0 = no pair
+    uint32_t key;
+    uint32_t ntied;
+};
+
+struct Boundary {  // one per rank, kBoundaryWords u32
+    uint32_t n_lo, n_hi;     // shard length
+    uint32_t first[3];       // first min(3, n) tokens
+    uint32_t last[2];        // last[1] = final token, last[0] = the one before (if n >= 2)
+    uint32_t trail_par;      // parity of the trailing run of best.left (x,x steps)
+    uint32_t all_a;          // the whole shard is a run of best.left
+    uint32_t pad[7];
+};
+static_assert(sizeof(Boundary) == kBoundaryWords * 4, "boundary layout");
+
+struct Halo {
+    uint32_t nl, nr;         // usable left / right context tokens
+    uint32_t L[2];           // L[1] is adjacent to the shard's first token
+    uint32_t R[3];           // R[0] is adjacent to the shard's last token
+    uint32_t par_in;         // parity of the run of `left` ending just before the shard
+};
+
+struct DevState {
+    unsigned long long n[2];  // token count of buffer 0 / 1
+    uint32_t done_step;       // first step that found no pair (0xFFFFFFFF = none)
+    uint32_t argmax_done;     // block completion counter of argmax_kernel (self-resetting)
+};
+
+struct TrainView {
+    uint16_t *tok[2];
+    DevState *dev;
+    PairTable main, delta;
+    Best *best;               // [max_merges + 1]
+    Best *partial;            // [kArgmaxBlocks]
+    uint32_t *tickets;        // [max_merges + 1] tile tickets, zero-initialised
+    unsigned long long *tile_status;  // [max tiles]
+    Boundary *boundary;       // this rank's boundary info (device)
+    int rank, world;
+};
+
+__device__ __forceinline__ uint32_t hash_key(uint32_t k) {
+    k ^= k >> 16;
+    k *= 0x7feb352dU;
+    k ^= k >> 15;
+    k *= 0x846ca68bU;
+    k ^= k >> 16;
+    return k;
+}
+
+__device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta) {
+    uint32_t slot = hash_key(key) & t.mask;
+    for (uint32_t probes = 0; probes <= t.mask; probes++) {
+        uint32_t k = t.keys[slot];
+        if (k == kEmptyKey) {
+            uint32_t old = atomicCAS(&t.keys[slot], kEmptyKey, key);
+            if (old == kEmptyKey) { atomicAdd(t.used, 1u); k = key; } else { k = old; }
+        }
+        if (k == key) {
+            atomicAdd(&t.cnt[slot], (unsigned long long)delta);
+            return;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+    atomicExch(t.overflow, 1u);
+}
+
+// All 32 lanes call; lanes with the same key are folded into one atomic.
+__device__ __forceinline__ void warp_table_add(const PairTable &t, bool valid, uint32_t key, long long delta) {
+    const unsigned m = __match_any_sync(0xffffffffu, valid ? key : kEmptyKey);
+    if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) table_add(t, key, delta * (long long)__popc(m));
+}
+
+__device__ __forceinline__ uint32_t mk(uint32_t l, uint32_t r) { return (l << 16) | r; }
+
+// ------------------------------------------------------------------ init / count
+
+__global__ void bytes_to_tokens_kernel(const uint8_t *__restrict__ text, uint16_t *__restrict__ tok, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) tok[i] = text[i];
+}
+
+// get_stats (lib.rs:28-48): all overlapping windows (i, i+1), i in [0, n-1), plus the
+// window that straddles into the next shard when right_tok is a token.  Block-private
+// shared-memory hash first (the initial corpus has few distinct, very hot pairs).
+constexpr int kCountSlots = 4096;
+__global__ void __launch_bounds__(256) count_kernel(const uint16_t *__restrict__ tok, uint64_t n, uint32_t right_tok,
+                                                    PairTable out) {
+    __shared__ uint32_t s_keys[kCountSlots];
+    __shared__ uint32_t s_cnt[kCountSlots];
+    for (int i = threadIdx.x; i < kCountSlots; i += blockDim.x) { s_keys[i] = kEmptyKey; s_cnt[i] = 0; }
+    __syncthreads();
+    const uint64_t nwin = n == 0 ? 0 : (n - 1) + (right_tok != kSentinel ? 1 : 0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (nwin + stride - 1) / stride;
+    for (uint64_t it = 0; it < rounds; it++) {
+        const uint64_t i = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < nwin;
+        uint32_t key = kEmptyKey;
+        if (valid) {
+            const uint32_t l = tok[i];
+            const uint32_t r = (i + 1 < n) ? (uint32_t)tok[i + 1] : right_tok;
+            key = mk(l, r);
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+            const uint32_t c = __popc(m);
+            uint32_t slot = hash_key(key) & (kCountSlots - 1);
+            bool placed = false;
+            for (int probes = 0; probes < 64; probes++) {
+                uint32_t k = s_keys[slot];
+                if (k == kEmptyKey) {
+                    uint32_t old = atomicCAS(&s_keys[slot], kEmptyKey, key);
+                    k = old == kEmptyKey ? key : old;
+                }
+                if (k == key) { atomicAdd(&s_cnt[slot], c); placed = true; break; }
+                slot = (slot + 1) & (kCountSlots - 1);
+            }
+            if (!placed) table_add(out, key, (long long)c);
+        }
+        // a block-private counter is 32 bit: flush long before it can wrap
+        if ((it & 0xFFFFF) == 0xFFFFF) {
+            __syncthreads();
+            for (int s = threadIdx.x; s < kCountSlots; s += blockDim.x)
+                if (s_keys[s] != kEmptyKey && s_cnt[s]) { table_add(out, s_keys[s], (long long)s_cnt[s]); s_cnt[s] = 0; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < kCountSlots; s += blockDim.x)
+        if (s_keys[s] != kEmptyKey && s_cnt[s]) table_add(out, s_keys[s], (long long)s_cnt[s]);
+}
+
+// ------------------------------------------------------------------ argmax
+
+__device__ __forceinline__ Best better(const Best &x, const Best &y) {
+    if (x.count != y.count) return x.count > y.count ? x : y;
+    if (x.count == 0) return x;
+    Best r = x.key < y.key ? x : y;
+    r.ntied = x.ntied + y.ntied;
+    return r;
+}
+
+__device__ __forceinline__ Best warp_best(Best v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best w;
+        w.count = __shfl_xor_sync(0xffffffffu, v.count, o);
+        w.key = __shfl_xor_sync(0xffffffffu, v.key, o);
+        w.ntied = __shfl_xor_sync(0xffffffffu, v.ntied, o);
+        v = better(v, w);
+    }
+    return v;
+}
+
+__device__ Best block_best(Best v) {
+    __shared__ Best s_w[32];
+    v = warp_best(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    Best r{0, kEmptyKey, 0};
+    if (warp == 0) {
+        if (lane < nw) r = s_w[lane];
+        r = warp_best(r);
+    }
+    return r;  // valid in warp 0
+}
+
+// lib.rs:92-94 with the deterministic tie rule.  The last block to finish folds the
+// partials into best[step] and prepares this rank's boundary record for that pair.
+__global__ void __launch_bounds__(256) argmax_kernel(TrainView v, uint32_t step) {
+    const PairTable &t = v.main;
+    Best mine{0, kEmptyKey, 0};
+    const uint64_t cap = (uint64_t)t.mask + 1;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = t.keys[s];
+        if (k == kEmptyKey) continue;
+        const unsigned long long c = t.cnt[s];
+        if (c == 0) continue;
+        mine = better(mine, Best{c, k, 1});
+    }
+    Best b = block_best(mine);
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        v.partial[blockIdx.x] = b;
+        __threadfence();
+        const uint32_t done = atomicAdd(&v.dev->argmax_done, 1u);
+        s_last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Best p{0, kEmptyKey, 0};
+    for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) p = better(p, v.partial[i]);
+    Best fin = block_best(p);
+    if (threadIdx.x == 0) {
+        v.best[step] = fin;
+        v.dev->argmax_done = 0;
+        if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+        // boundary record of this shard for the winning pair
+        const uint16_t *tok = v.tok[step & 1];
+        const unsigned long long n = v.dev->n[step & 1];
+        Boundary bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.n_lo = (uint32_t)n;
+        bd.n_hi = (uint32_t)(n >> 32);
+        for (int i = 0; i < 3; i++) bd.first[i] = (unsigned long long)i < n ? (uint32_t)tok[i] : kSentinel;
+        bd.last[1] = n >= 1 ? (uint32_t)tok[n - 1] : kSentinel;
+        bd.last[0] = n >= 2 ? (uint32_t)tok[n - 2] : kSentinel;
+        const uint32_t a = fin.key >> 16, bb = fin.key & 0xFFFFu;
+        if (fin.count != 0 && a == bb && v.world > 1) {
+            unsigned long long run = 0;
+            while (run < n && tok[n - 1 - run] == a) run++;
+            bd.trail_par = (uint32_t)(run & 1);
+            bd.all_a = run == n ? 1u : 0u;
+        }
+        *v.boundary = bd;
+    }
+}
+
+// ------------------------------------------------------------------ merge
+
+// tile status word: [63:62] flag (1 = aggregate, 2 = inclusive prefix) | [61:42] step + 1 | [41:0] count
+constexpr unsigned long long kCountMask = (1ull << 42) - 1;
+__device__ __forceinline__ unsigned long long pack_status(uint32_t flag, uint32_t step, unsigned long long count) {
+    return ((unsigned long long)flag << 62) | ((unsigned long long)((step + 1) & 0xFFFFF) << 42) | (count & kCountMask);
+}
+
+__device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, uint32_t b) {
+    Halo h;
+    h.nl = h.nr = 0;
+    h.L[0] = h.L[1] = kSentinel;
+    h.R[0] = h.R[1] = h.R[2] = kSentinel;
+    h.par_in = 0;
+    if (world <= 1 || all == nullptr) return h;
+    // left context: the last two tokens of the stream before this shard
+    uint32_t got[2];
+    int ng = 0;
+    for (int r = rank - 1; r >= 0 && ng < 2; r--) {
+        const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
+        if (n >= 1) got[ng++] = all[r].last[1];
+        if (n >= 2 && ng < 2) got[ng++] = all[r].last[0];
+    }
+    h.nl = ng;
+    if (ng >= 1) h.L[1] = got[0];
+    if (ng >= 2) h.L[0] = got[1];
+    // right context: the first three tokens of the stream after this shard
+    int nr = 0;
+    for (int r = rank + 1; r < world && nr < 3; r++) {
+        const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
+        for (int i = 0; i < 3 && (unsigned long long)i < n && nr < 3; i++) h.R[nr++] = all[r].first[i];
+    }
+    h.nr = nr;
+    if (a == b) {
+        uint32_t par = 0;
+        for (int r = rank - 1; r >= 0; r--) {
+            const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
+            if (n == 0) continue;
+            if (all[r].all_a) { par ^= (uint32_t)(n & 1); continue; }
+            par ^= all[r].trail_par;
+            break;
+        }
+        h.par_in = par;
+    }
+    return h;
+}
+
+// merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
+__global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
+                                                     PairTable upd) {
+    const Best bb = v.best[step];
+    if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
+    const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
+    const uint16_t *__restrict__ in = v.tok[step & 1];
+    uint16_t *__restrict__ out = v.tok[(step + 1) & 1];
+    const long long n = (long long)v.dev->n[step & 1];
+    const long long ntiles = n == 0 ? 1 : (n + kTile - 1) / kTile;
+    const bool same = a == b;
+
+    __shared__ Halo s_halo;
+    __shared__ long long s_tile;
+    __shared__ uint16_t s_edge[kTPB][6];          // per thread: first 3, last 2 tokens (+pad)
+    __shared__ long long s_scan[kTPB / 32];
+    __shared__ long long s_lastnon[kTPB / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_tile_lastnon;
+    __shared__ uint16_t s_out[kTile];
+
+    if (threadIdx.x == 0) s_halo = make_halo(all_bd, v.rank, v.world, a, b);
+    __syncthreads();
+    const Halo h = s_halo;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // token at global (shard-local) position p, including halo context
+    auto tok_at = [&](long long p) -> uint32_t {
+        if (p >= 0 && p < n) return in[p];
+        if (p < 0) return (-p <= (long long)h.nl) ? h.L[2 + p] : kSentinel;
+        const long long q = p - n;
+        return q < (long long)h.nr ? h.R[q] : kSentinel;
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&v.tickets[step], 1u);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) break;
+        const long long tbase = tile * kTile;
+        const long long base = tbase + (long long)threadIdx.x * kIPT;
+
+        // ---- load 16 tokens per thread (sentinel beyond the end) ----
+        uint32_t e[kIPT + 5];  // e[2 + i] = token base + i ; e[0..1] left context ; e[18..20] right context
+        if (base + kIPT <= n) {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(in + base);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(in + base + 8);
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) { e[2 + 2 * i] = w[i] & 0xFFFFu; e[3 + 2 * i] = w[i] >> 16; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kIPT; i++) e[2 + i] = (base + i < n) ? (uint32_t)in[base + i] : kSentinel;
+        }
+        s_edge[threadIdx.x][0] = (uint16_t)e[2];
+        s_edge[threadIdx.x][1] = (uint16_t)e[3];
+        s_edge[threadIdx.x][2] = (uint16_t)e[4];
+        s_edge[threadIdx.x][3] = (uint16_t)e[2 + kIPT - 2];
+        s_edge[threadIdx.x][4] = (uint16_t)e[2 + kIPT - 1];
+        __syncthreads();
+        if (threadIdx.x > 0) {
+            e[0] = s_edge[threadIdx.x - 1][3];
+            e[1] = s_edge[threadIdx.x - 1][4];
+        } else {
+            e[0] = tok_at(base - 2);
+            e[1] = tok_at(base - 1);
+        }
+        if (threadIdx.x < kTPB - 1 && base + kIPT + 3 <= n) {
+            e[18] = s_edge[threadIdx.x + 1][0];
+            e[19] = s_edge[threadIdx.x + 1][1];
+            e[20] = s_edge[threadIdx.x + 1][2];
+        } else {
+            // tile edge or near the end of the shard: positions >= n come from the right halo
+            e[18] = tok_at(base + kIPT);
+            e[19] = tok_at(base + kIPT + 1);
+            e[20] = tok_at(base + kIPT + 2);
+        }
+        // positions >= n inside this thread's own range must also see the right halo
+        if (base + kIPT > n) {
+#pragma unroll
+            for (int i = 0; i < kIPT; i++)
+                if (base + i >= n) e[2 + i] = tok_at(base + i);
+        }
+
+        // ---- (x,x): run offset parity needs the position of the last non-x before each token ----
+        long long run_start = 0;  // start of the x-run that is open when this thread's range begins
+        if (same) {
+            long long lastnon = -1;  // last position in this thread's range holding a non-x token (LLONG_MIN-ish = none)
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < kIPT; i++)
+                if (base + i < n && e[2 + i] != a) { lastnon = base + i; any = true; }
+            long long val = any ? lastnon : -(1ll << 62);
+            // inclusive max-scan across the block
+            long long x = val;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x = max(x, y);
+            }
+            if (lane == 31) s_lastnon[warp] = x;
+            // warp 0 additionally scans backwards from the tile start for the run entering the tile
+            if (warp == 0) {
+                long long found = -(1ll << 62);
+                bool hit = false;
+                for (long long p = tbase - 1; p >= 0 && !hit; p -= 32) {
+                    const long long q = p - lane;
+                    const bool non = q >= 0 && in[q] != a;
+                    const unsigned m = __ballot_sync(0xffffffffu, non);
+                    if (m) { found = p - (__ffs(m) - 1); hit = true; }
+                }
+                // reached the shard start inside the run: continue it virtually by par_in elements
+                if (!hit) found = -1 - (long long)h.par_in;
+                if (lane == 0) s_tile_lastnon = found;
+            }
+            __syncthreads();
+            long long before = s_tile_lastnon;  // last non-x position before this thread's range
+            for (int w = 0; w < warp; w++) before = max(before, s_lastnon[w]);
+            const long long xe = __shfl_up_sync(0xffffffffu, x, 1);
+            if (lane > 0) before = max(before, xe);
+            run_start = before + 1;
+        }
+
+        // ---- sites and removed flags ----
+        uint32_t site = 0, removed = 0;  // bit i = position base + i
+        {
+            long long rs = run_start;
+#pragma unroll
+            for (int i = 0; i < kIPT; i++) {
+                const long long p = base + i;
+                const bool valid = p < n;
+                bool st, rm;
+                if (same) {
+                    const bool isa = e[2 + i] == a;
+                    const bool odd = ((p - rs) & 1) != 0;
+                    st = valid && isa && !odd && e[3 + i] == a;
+                    rm = valid && isa && odd;
+                    if (!isa) rs = p + 1;
+                } else {
+                    st = valid && e[2 + i] == a && e[3 + i] == b;
+                    rm = valid && e[1 + i] == a && e[2 + i] == b;
+                }
+                site |= (st ? 1u : 0u) << i;
+                removed |= (rm ? 1u : 0u) << i;
+            }
+        }
+        // (a != b, first token of the shard): e[1] is the left halo, handled by the general rule.
+
+        // ---- histogram patches at the sites (see oracle/ecgb_oracle.c ecgo_train_fast) ----
+#pragma unroll 1
+        for (int i = 0; i < kIPT; i++) {
+            const bool st = (site >> i) & 1u;
+            if (!__any_sync(0xffffffffu, st)) continue;
+            const uint32_t tm2 = e[i], tm1 = e[1 + i], tp2 = e[4 + i], tp3 = e[5 + i];
+            const bool has_left = st && tm1 != kSentinel;
+            const bool prev_site = has_left && tm2 == a && tm1 == b;      // site at p-2 (parity is implied)
+            const bool has_right = st && tp2 != kSentinel;
+            const bool next_site = has_right && tp2 == a && tp3 == b;     // site at p+2
+            warp_table_add(upd, st, mk(a, b), -1);
+            warp_table_add(upd, has_left, mk(tm1, a), -1);
+            warp_table_add(upd, has_left, mk(prev_site ? z : tm1, z), +1);
+            warp_table_add(upd, has_right && !next_site, mk(b, tp2), -1);
+            warp_table_add(upd, has_right && !next_site, mk(z, tp2), +1);
+        }
+
+        // ---- compaction: kept tokens -> shared staging -> coalesced stores ----
+        uint32_t nvalid = (base >= n) ? 0u : (uint32_t)min((long long)kIPT, n - base);
+        const uint32_t validmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        const uint32_t keepmask = validmask & ~removed;
+        const int kept = __popc(keepmask);
+        int incl = kept;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int warp_off = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < kTPB / 32; w++) {
+            const int c = (int)s_scan[w];
+            if (w < warp) warp_off += c;
+            tile_total += c;
+        }
+        int o = warp_off + incl - kept;
+#pragma unroll
+        for (int i = 0; i < kIPT; i++)
+            if ((keepmask >> i) & 1u) s_out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[2 + i]);
+
+        // decoupled look-back over the tiles that precede this one
+        if (threadIdx.x == 0) {
+            unsigned long long excl = 0;
+            if (tile > 0) {
+                atomicExch(&v.tile_status[tile], pack_status(1, step, (unsigned long long)tile_total));
+                long long j = tile - 1;
+                for (;;) {
+                    const unsigned long long sdw = atomicAdd(&v.tile_status[j], 0ull);
+                    const uint32_t flag = (uint32_t)(sdw >> 62);
+                    const uint32_t ep = (uint32_t)((sdw >> 42) & 0xFFFFF);
+                    if (flag == 0 || ep != ((step + 1) & 0xFFFFF)) continue;  // not published yet for this step
+                    excl += sdw & kCountMask;
+                    if (flag == 2) break;
+                    j--;
+                }
+            }
+            __threadfence();
+            atomicExch(&v.tile_status[tile], pack_status(2, step, excl + (unsigned long long)tile_total));
+            s_prefix = excl;
+            if (tile == ntiles - 1) v.dev->n[(step + 1) & 1] = excl + (unsigned long long)tile_total;
+        }
+        __syncthreads();
+        const unsigned long long gofs = s_prefix;
+        for (int k = threadIdx.x; k < tile_total; k += kTPB) out[gofs + k] = s_out[k];
+    }
+}
+
+// ------------------------------------------------------------------ delta lists (sharded training)
+
+// list layout (u32 words): [0] count, [1] overflow, [2..3] pad, then cap keys, then cap 64-bit deltas
+__global__ void compact_delta_kernel(PairTable d, uint32_t *list, uint32_t cap) {
+    uint32_t *keys = list + 4;
+    long long *deltas = reinterpret_cast<long long *>(list + 4 + cap);
+    const uint64_t n = (uint64_t)d.mask + 1;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = d.keys[s];
+        if (k == kEmptyKey) continue;
+        const long long c = (long long)d.cnt[s];
+        d.keys[s] = kEmptyKey;
+        d.cnt[s] = 0;
+        if (c == 0) continue;
+        const uint32_t at = atomicAdd(&list[0], 1u);
+        if (at < cap) { keys[at] = k; deltas[at] = c; } else { list[1] = 1; }
+    }
+}
+
+__global__ void reset_list_kernel(uint32_t *list, uint32_t *used) { list[0] = 0; list[1] = 0; list[2] = 0; list[3] = 0; *used = 0; }
+
+__global__ void apply_lists_kernel(PairTable main, const uint32_t *__restrict__ lists, uint32_t list_words, uint32_t cap,
+                                   int world) {
+    for (int r = 0; r < world; r++) {
+        const uint32_t *list = lists + (size_t)r * list_words;
+        const uint32_t cnt = min(list[0], cap);
+        if (list[1]) atomicExch(main.overflow, 2u);
+        const uint32_t *keys = list + 4;
+        const long long *deltas = reinterpret_cast<const long long *>(list + 4 + cap);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+            table_add(main, keys[i], deltas[i]);
+    }
+}
+
+__global__ void widen_ids_kernel(const uint16_t *__restrict__ tok, uint32_t *__restrict__ out, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = tok[i];
+}
+
+}  // namespace ecgb
+
+using namespace ecgb;
+
+struct ecgb_trainer {
+    int device = 0;
+    int sms = 148;
+    uint64_t capacity = 0;
+    uint32_t max_merges = 0;
+    uint32_t list_cap = 0;
+    uint32_t steps_done = 0;   // merge steps applied so far
+    uint32_t argmax_for = 0;   // best[] entries computed so far
+    bool loaded = false;
+    TrainView v{};
+    void *blocks[16] = {nullptr};
+    int n_blocks = 0;
+    uint32_t *d_list = nullptr;  // this rank's delta list
+};
+
+static int dev_alloc(ecgb_trainer *t, void **p, size_t bytes, bool zero) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(ECGB_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    t->blocks[t->n_blocks++] = *p;
+    if (zero) {
+        e = cudaMemset(*p, 0, bytes);
+        if (e != cudaSuccess) return fail(ECGB_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    return ECGB_OK;
+}
+
+static int alloc_table(ecgb_trainer *t, PairTable *pt, uint32_t log2cap) {
+    const size_t cap = (size_t)1 << log2cap;
+    int rc;
+    if ((rc = dev_alloc(t, (void **)&pt->keys, cap * 4, false))) return rc;
+    if ((rc = dev_alloc(t, (void **)&pt->cnt, cap * 8, true))) return rc;
+    if ((rc = dev_alloc(t, (void **)&pt->used, 8, true))) return rc;
+    pt->overflow = pt->used + 1;
+    pt->mask = (uint32_t)(cap - 1);
+    cudaError_t e = cudaMemset(pt->keys, 0xFF, cap * 4);
+    if (e != cudaSuccess) return fail(ECGB_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_t max_merges, uint32_t table_log2,
+                                   ecgb_trainer **out) {
+    ECGB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    ECGB_REQUIRE(max_merges <= 0xFFFE - 256, "max_merges %u exceeds the 16-bit token id space", max_merges);
+    ECGB_REQUIRE(capacity_tokens < (1ull << 41), "capacity too large");
+    ECGB_REQUIRE(table_log2 == 0 || (table_log2 >= 10 && table_log2 <= 28), "table_log2 must be 0 (default) or in [10, 28]");
+    int rc = check_device(device);
+    if (rc) return rc;
+    ecgb_trainer *t = new (std::nothrow) ecgb_trainer();
+    if (!t) return fail(ECGB_ENOMEM, "host allocation failed");
+    t->device = device;
+    t->sms = sm_count(device);
+    t->capacity = capacity_tokens;
+    t->max_merges = max_merges;
+    t->list_cap = 1u << 15;
+    DeviceGuard g(device);
+    const size_t tokbytes = (capacity_tokens + 64) * 2;
+    const size_t ntiles = (size_t)(capacity_tokens / kTile) + 2;
+    if (table_log2 == 0) table_log2 = 22;
+    rc = dev_alloc(t, (void **)&t->v.tok[0], tokbytes, false);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.tok[1], tokbytes, false);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.dev, sizeof(DevState), true);
+    if (!rc) rc = alloc_table(t, &t->v.main, table_log2);
+    if (!rc) rc = alloc_table(t, &t->v.delta, 18);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.best, sizeof(Best) * ((size_t)max_merges + 1), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * kArgmaxBlocks, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.tickets, 4 * ((size_t)max_merges + 1), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.tile_status, 8 * ntiles, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->d_list, (size_t)(4 + 3 * (size_t)t->list_cap) * 4, true);
+    if (rc) { ecgb_trainer_destroy(t); return rc; }
+    t->v.rank = 0;
+    t->v.world = 1;
+    *out = t;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_destroy(ecgb_trainer *t) {
+    if (!t) return ECGB_OK;
+    {
+        DeviceGuard g(t->device);
+        for (int i = 0; i < t->n_blocks; i++) cudaFree(t->blocks[i]);
+    }
+    delete t;
+    return ECGB_OK;
+}
+
+static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
+    DevState h{};
+    h.n[0] = n; h.n[1] = 0; h.done_step = 0xFFFFFFFFu; h.argmax_done = 0;
+    ECGB_CUDA(cudaMemcpyAsync(t->v.dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));  // h is a stack object
+    const size_t cap = (size_t)t->v.main.mask + 1;
+    ECGB_CUDA(cudaMemsetAsync(t->v.main.keys, 0xFF, cap * 4, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.main.cnt, 0, cap * 8, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.main.used, 0, 8, st));
+    const size_t dcap = (size_t)t->v.delta.mask + 1;
+    ECGB_CUDA(cudaMemsetAsync(t->v.delta.keys, 0xFF, dcap * 4, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.delta.cnt, 0, dcap * 8, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.delta.used, 0, 8, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.tickets, 0, 4 * ((size_t)t->max_merges + 1), st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.best, 0, sizeof(Best) * ((size_t)t->max_merges + 1), st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.tile_status, 0, 8 * ((size_t)(t->capacity / kTile) + 2), st));
+    t->steps_done = 0;
+    t->argmax_for = 0;
+    t->loaded = true;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_load_device(ecgb_trainer *t, const uint8_t *d_text, uint64_t n, void *stream) {
+    ECGB_REQUIRE(t, "trainer is NULL");
+    ECGB_REQUIRE(n <= t->capacity, "corpus of %llu bytes exceeds the trainer capacity %llu", (unsigned long long)n,
+                 (unsigned long long)t->capacity);
+    ECGB_REQUIRE(n == 0 || d_text, "d_text is NULL");
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    int rc = reset_state(t, n, st);
+    if (rc) return rc;
+    if (n) {
+        bytes_to_tokens_kernel<<<t->sms * 8, 256, 0, st>>>(d_text, t->v.tok[0], n);
+        ECGB_CUDA(cudaGetLastError());
+    }
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_load_host(ecgb_trainer *t, const uint8_t *h_text, uint64_t n) {
+    ECGB_REQUIRE(t, "trainer is NULL");
+    ECGB_REQUIRE(n <= t->capacity, "corpus of %llu bytes exceeds the trainer capacity %llu", (unsigned long long)n,
+                 (unsigned long long)t->capacity);
+    ECGB_REQUIRE(n == 0 || h_text, "h_text is NULL");
+    DeviceGuard g(t->device);
+    // stage the bytes in the (not yet used) second token buffer
+    uint8_t *d_bytes = reinterpret_cast<uint8_t *>(t->v.tok[1]);
+    if (n) ECGB_CUDA(cudaMemcpy(d_bytes, h_text, n, cudaMemcpyHostToDevice));
+    int rc = ecgb_trainer_load_device(t, d_bytes, n, nullptr);
+    if (rc) return rc;
+    ECGB_CUDA(cudaStreamSynchronize(0));
+    return ECGB_OK;
+}
+
+static int check_tables(ecgb_trainer *t) {
+    uint32_t flags[2] = {0, 0};
+    ECGB_CUDA(cudaMemcpy(flags, t->v.main.used, 8, cudaMemcpyDeviceToHost));
+    if (flags[1]) return fail(ECGB_ECAPACITY, "pair table overflow (code %u): %u of %u slots used; raise table_log2", flags[1],
+                              flags[0], t->v.main.mask + 1);
+    uint32_t dflags[2] = {0, 0};
+    ECGB_CUDA(cudaMemcpy(dflags, t->v.delta.used, 8, cudaMemcpyDeviceToHost));
+    if (dflags[1]) return fail(ECGB_ECAPACITY, "delta table overflow");
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *h_pairs, uint64_t *h_counts,
+                                uint32_t *h_ntied, uint32_t *n_done) {
+    ECGB_REQUIRE(t && n_done, "NULL argument");
+    *n_done = 0;
+    ECGB_REQUIRE(t->loaded, "no corpus loaded");
+    ECGB_REQUIRE(t->v.world == 1, "ecgb_trainer_run is the single-device loop; use the dist_* calls for shards");
+    ECGB_REQUIRE(t->steps_done == 0, "trainer already ran; load the corpus again");
+    ECGB_REQUIRE(num_merges <= t->max_merges, "num_merges %u > max_merges %u", num_merges, t->max_merges);
+    DeviceGuard g(t->device);
+    cudaStream_t st = 0;
+    uint64_t n0 = 0;
+    ECGB_CUDA(cudaMemcpy(&n0, &t->v.dev->n[0], 8, cudaMemcpyDeviceToHost));
+    // get_stats once; afterwards the histogram is patched by the merge passes
+    count_kernel<<<t->sms * 4, 256, 0, st>>>(t->v.tok[0], n0, kSentinel, t->v.main);
+    ECGB_CUDA(cudaGetLastError());
+    const int merge_grid = (int)std::min<uint64_t>((uint64_t)t->sms * 6, n0 / kTile + 1);
+    for (uint32_t step = 0; step < num_merges; step++) {
+        argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
+        merge_kernel<<<merge_grid, kTPB, 0, st>>>(t->v, step, nullptr, t->v.main);
+        if ((step & 255) == 255) ECGB_CUDA(cudaGetLastError());
+    }
+    ECGB_CUDA(cudaGetLastError());
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    int rc = check_tables(t);
+    if (rc) return rc;
+    DevState hs;
+    ECGB_CUDA(cudaMemcpy(&hs, t->v.dev, sizeof(hs), cudaMemcpyDeviceToHost));
+    const uint32_t done = std::min(num_merges, hs.done_step);
+    t->steps_done = done;
+    t->argmax_for = num_merges;
+    std::vector<Best> hb(done ? done : 1);
+    if (done) ECGB_CUDA(cudaMemcpy(hb.data(), t->v.best, sizeof(Best) * done, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < done; i++) {
+        if (h_pairs) { h_pairs[2 * i] = hb[i].key >> 16; h_pairs[2 * i + 1] = hb[i].key & 0xFFFFu; }
+        if (h_counts) h_counts[i] = hb[i].count;
+        if (h_ntied) h_ntied[i] = hb[i].ntied;
+    }
+    *n_done = done;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_length(ecgb_trainer *t, uint64_t *n_out) {
+    ECGB_REQUIRE(t && n_out, "NULL argument");
+    DeviceGuard g(t->device);
+    ECGB_CUDA(cudaDeviceSynchronize());
+    DevState hs;
+    ECGB_CUDA(cudaMemcpy(&hs, t->v.dev, sizeof(hs), cudaMemcpyDeviceToHost));
+    *n_out = hs.n[t->steps_done & 1];
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t cap, uint64_t *n_out) {
+    ECGB_REQUIRE(t && n_out, "NULL argument");
+    uint64_t n = 0;
+    int rc = ecgb_trainer_length(t, &n);
+    if (rc) return rc;
+    *n_out = n;
+    if (n > cap) return fail(ECGB_ECAPACITY, "ids buffer too small: need %llu", (unsigned long long)n);
+    if (n == 0) return ECGB_OK;
+    ECGB_REQUIRE(h_ids, "h_ids is NULL");
+    DeviceGuard g(t->device);
+    // widen in chunks through the idle token buffer
+    uint32_t *d_tmp = reinterpret_cast<uint32_t *>(t->v.tok[(t->steps_done + 1) & 1]);
+    const uint64_t chunk_cap = (t->capacity + 64) / 2;
+    const uint16_t *src = t->v.tok[t->steps_done & 1];
+    for (uint64_t o = 0; o < n; o += chunk_cap) {
+        const uint64_t c = std::min(chunk_cap, n - o);
+        widen_ids_kernel<<<t->sms * 8, 256>>>(src + o, d_tmp, c);
+        ECGB_CUDA(cudaGetLastError());
+        ECGB_CUDA(cudaMemcpy(h_ids + o, d_tmp, c * 4, cudaMemcpyDeviceToHost));
+    }
+    return ECGB_OK;
+}
+
+// ------------------------------------------------------------------ sharded (step-wise) interface
+
+extern "C" int ecgb_trainer_dist_sizes(const ecgb_trainer *t, uint32_t *boundary_bytes, uint32_t *list_bytes) {
+    ECGB_REQUIRE(t && boundary_bytes && list_bytes, "NULL argument");
+    *boundary_bytes = kBoundaryWords * 4;
+    *list_bytes = (4 + 3 * t->list_cap) * 4;
+    return ECGB_OK;
+}
+
+// Declare this trainer to be shard `rank` of `world`, and publish its boundary record
+// (no pair selected yet) to d_boundary_out.
+extern "C" int ecgb_trainer_dist_begin(ecgb_trainer *t, int rank, int world, void *d_boundary_out, void *stream) {
+    ECGB_REQUIRE(t && d_boundary_out, "NULL argument");
+    ECGB_REQUIRE(t->loaded && t->steps_done == 0, "load the shard first");
+    ECGB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+    t->v.rank = rank;
+    t->v.world = world;
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    // an argmax over the (still empty) table just writes the boundary record: count == 0 pair
+    TrainView v = t->v;
+    v.best = t->v.best + t->max_merges;  // scratch slot
+    argmax_kernel<<<1, 256, 0, st>>>(v, 0);
+    ECGB_CUDA(cudaGetLastError());
+    // the scratch argmax recorded "done" because the table is empty: clear that
+    const uint32_t none = 0xFFFFFFFFu;
+    ECGB_CUDA(cudaMemcpyAsync(&t->v.dev->done_step, &none, 4, cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaMemcpyAsync(d_boundary_out, t->v.boundary, sizeof(Boundary), cudaMemcpyDeviceToDevice, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    return ECGB_OK;
+}
+
+// Local get_stats of this shard (including the window that straddles into the next
+// shard) as a delta list in d_list_out.
+extern "C" int ecgb_trainer_dist_count(ecgb_trainer *t, const void *d_all_boundaries, void *d_list_out, void *stream) {
+    ECGB_REQUIRE(t && d_all_boundaries && d_list_out, "NULL argument");
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    // the right neighbour token is needed on the host side of the launch: read the gathered records
+    std::vector<Boundary> all((size_t)t->v.world);
+    ECGB_CUDA(cudaMemcpyAsync(all.data(), d_all_boundaries, sizeof(Boundary) * all.size(), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    uint32_t right = kSentinel;
+    for (int r = t->v.rank + 1; r < t->v.world; r++) {
+        const uint64_t n = ((uint64_t)all[r].n_hi << 32) | all[r].n_lo;
+        if (n) { right = all[r].first[0]; break; }
+    }
+    const uint64_t n = ((uint64_t)all[t->v.rank].n_hi << 32) | all[t->v.rank].n_lo;
+    uint32_t *list = static_cast<uint32_t *>(d_list_out);
+    reset_list_kernel<<<1, 1, 0, st>>>(list, t->v.delta.used);
+    count_kernel<<<t->sms * 4, 256, 0, st>>>(t->v.tok[0], n, right, t->v.delta);
+    compact_delta_kernel<<<t->sms * 2, 256, 0, st>>>(t->v.delta, list, t->list_cap);
+    ECGB_CUDA(cudaGetLastError());
+    return ECGB_OK;
+}
+
+// Apply every rank's delta list to this rank's copy of the global histogram, take the
+// argmax for `step` and publish this shard's boundary record for the winning pair.
+extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const void *d_all_lists, void *d_boundary_out,
+                                        void *stream) {
+    ECGB_REQUIRE(t && d_all_lists && d_boundary_out, "NULL argument");
+    ECGB_REQUIRE(step <= t->max_merges, "step %u out of range", step);
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    const uint32_t list_words = 4 + 3 * t->list_cap;
+    apply_lists_kernel<<<t->sms, 256, 0, st>>>(t->v.main, static_cast<const uint32_t *>(d_all_lists), list_words,
+                                               t->list_cap, t->v.world);
+    argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
+    ECGB_CUDA(cudaGetLastError());
+    ECGB_CUDA(cudaMemcpyAsync(d_boundary_out, t->v.boundary, sizeof(Boundary), cudaMemcpyDeviceToDevice, st));
+    t->argmax_for = step + 1;
+    return ECGB_OK;
+}
+
+// Merge best[step] in this shard given every rank's boundary record; the histogram
+// patches go to d_list_out.
+extern "C" int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const void *d_all_boundaries, void *d_list_out,
+                                       void *stream) {
+    ECGB_REQUIRE(t && d_all_boundaries && d_list_out, "NULL argument");
+    ECGB_REQUIRE(step < t->max_merges, "step %u out of range", step);
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    uint32_t *list = static_cast<uint32_t *>(d_list_out);
+    reset_list_kernel<<<1, 1, 0, st>>>(list, t->v.delta.used);
+    const int merge_grid = (int)std::min<uint64_t>((uint64_t)t->sms * 6, t->capacity / kTile + 1);
+    merge_kernel<<<merge_grid, kTPB, 0, st>>>(t->v, step, static_cast<const Boundary *>(d_all_boundaries), t->v.delta);
+    compact_delta_kernel<<<t->sms * 2, 256, 0, st>>>(t->v.delta, list, t->list_cap);
+    ECGB_CUDA(cudaGetLastError());
+    t->steps_done = step + 1;
+    return ECGB_OK;
+}
+
+// Synchronise and read back the merges chosen so far (steps [0, n_steps)).
+extern "C" int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t *h_pairs, uint64_t *h_counts,
+                                    uint32_t *h_ntied, uint32_t *n_done) {
+    ECGB_REQUIRE(t && n_done, "NULL argument");
+    ECGB_REQUIRE(n_steps <= t->max_merges, "n_steps out of range");
+    DeviceGuard g(t->device);
+    ECGB_CUDA(cudaDeviceSynchronize());
+    int rc = check_tables(t);
+    if (rc) return rc;
+    DevState hs;
+    ECGB_CUDA(cudaMemcpy(&hs, t->v.dev, sizeof(hs), cudaMemcpyDeviceToHost));
+    const uint32_t done = std::min(n_steps, hs.done_step);
+    t->steps_done = std::min(t->steps_done, done);
+    std::vector<Best> hb(done ? done : 1);
+    if (done) ECGB_CUDA(cudaMemcpy(hb.data(), t->v.best, sizeof(Best) * done, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < done; i++) {
+        if (h_pairs) { h_pairs[2 * i] = hb[i].key >> 16; h_pairs[2 * i + 1] = hb[i].key & 0xFFFFu; }
+        if (h_counts) h_counts[i] = hb[i].count;
+        if (h_ntied) h_ntied[i] = hb[i].ntied;
+    }
+    *n_done = done;
+    return ECGB_OK;
+}

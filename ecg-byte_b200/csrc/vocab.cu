@@ -1,0 +1,230 @@
+// E1: trie construction (reference: rust_bpe/src/lib.rs:127-147 TrieNode, 153-161 build).
+//
+// The reference rebuilds a HashMap-of-HashMaps trie on every encode_text call.  Here
+// the trie is built once per vocabulary on the host, renumbered breadth-first so the
+// children of a node are contiguous, and flattened into bitmap nodes that stay
+// resident on the device:
+//   compact node (8 bytes, alphabets of <= 31 symbol classes -- every ECG-Byte
+//   vocabulary: 26 letters):  x = child bitmap over classes,
+//                             y = first_child << 16 | token_id (0xFFFF = not a token)
+//   child(c) = first_child + popc(bitmap & ((1 << c) - 1))          -- no hashing, one
+//   8-byte shared-memory load per trie step.
+//   wide node (40 bytes, any byte alphabet): 256-bit bitmap, first_child, token_id.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "common.h"
+
+namespace ecgb {
+
+struct HostNode {
+    std::map<uint32_t, int> child;  // ordered by symbol
+    int64_t token = -1;
+};
+
+struct HostTrie {
+    std::vector<HostNode> nodes;
+    uint32_t max_len = 1;
+    int insert(const uint32_t *seq, size_t len, uint32_t id) {
+        int n = 0;
+        for (size_t i = 0; i < len; i++) {
+            auto it = nodes[n].child.find(seq[i]);
+            if (it == nodes[n].child.end()) {
+                nodes.emplace_back();
+                int c = (int)nodes.size() - 1;
+                nodes[n].child[seq[i]] = c;
+                n = c;
+            } else {
+                n = it->second;
+            }
+        }
+        nodes[n].token = id;  // lib.rs:145: later insert overwrites
+        return n;
+    }
+};
+
+}  // namespace ecgb
+
+struct ecgb_vocab {
+    int device = 0;
+    ecgb_vocab_info_t info{};
+    ecgb::VocabView view{};
+    void *d_nodes = nullptr;
+    uint8_t *d_cls = nullptr;
+    uint8_t h_cls[256];
+    // host copy of the expanded sequences (decode, pickles)
+    std::vector<uint32_t> seq;
+    std::vector<uint64_t> seq_off;
+    std::vector<uint32_t> ids;
+};
+
+const ecgb::VocabView *ecgb_vocab_view(const ecgb_vocab *v) { return &v->view; }
+int ecgb_vocab_device(const ecgb_vocab *v) { return v->device; }
+
+using namespace ecgb;
+
+extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_off, const uint32_t *h_ids,
+                                 uint32_t n_merges, int device, ecgb_vocab **out) {
+    ECGB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    ECGB_REQUIRE(n_merges == 0 || (h_seq && h_seq_off && h_ids), "NULL merge arrays");
+    int rc = check_device(device);
+    if (rc) return rc;
+
+    HostTrie t;
+    t.nodes.reserve(1024 + (size_t)n_merges * 4);
+    t.nodes.emplace_back();
+    for (uint32_t b = 0; b < 256; b++) t.insert(&b, 1, b);  // lib.rs:155-157
+    for (uint32_t i = 0; i < n_merges; i++) {               // lib.rs:159-161
+        uint64_t o = h_seq_off[i], e = h_seq_off[i + 1];
+        ECGB_REQUIRE(e >= o, "seq_off is not non-decreasing at merge %u", i);
+        ECGB_REQUIRE(e > o, "merge %u has an empty sequence", i);
+        for (uint64_t k = o; k < e; k++)
+            ECGB_REQUIRE(h_seq[k] < 256, "merge %u: sequence element %u is not a byte", i, h_seq[k]);
+        t.insert(h_seq + o, (size_t)(e - o), h_ids[i]);
+        t.max_len = std::max<uint32_t>(t.max_len, (uint32_t)(e - o));
+    }
+
+    // ---- symbol classes: a..z -> 0..25, other bytes that need a trie edge -> 26.. ----
+    bool needs[256] = {false};
+    for (size_t n = 0; n < t.nodes.size(); n++) {
+        for (auto &kv : t.nodes[n].child) {
+            const HostNode &c = t.nodes[kv.second];
+            if (n != 0) needs[kv.first] = true;                              // edge below depth 1
+            else if (!c.child.empty() || c.token != (int64_t)kv.first) needs[kv.first] = true;
+        }
+    }
+    uint8_t cls[256];
+    std::memset(cls, 31, sizeof(cls));
+    for (int k = 0; k < kNumSymbols; k++) cls['a' + k] = (uint8_t)k;
+    int n_classes = kNumSymbols;
+    bool compact = true;
+    for (int b = 0; b < 256; b++) {
+        if (!needs[b] || (b >= 'a' && b <= 'z')) continue;
+        if (n_classes >= 31) { compact = false; break; }
+        cls[b] = (uint8_t)n_classes++;
+    }
+    int64_t max_tok = 255;
+    for (auto &nd : t.nodes) max_tok = std::max(max_tok, nd.token);
+    if (max_tok >= 0xFFFF) compact = false;
+
+    ecgb_vocab *v = new (std::nothrow) ecgb_vocab();
+    if (!v) return fail(ECGB_ENOMEM, "host allocation failed");
+    v->device = device;
+
+    // ---- breadth-first renumbering ----
+    std::vector<int> order;  // new index -> old index
+    std::vector<uint32_t> first_child;
+    order.reserve(t.nodes.size());
+    order.push_back(0);
+    size_t n_total = 0;
+    std::vector<uint32_t> words;
+    for (int pass = 0; pass < 2; pass++) {
+        // pass 0: try compact (may overflow 16-bit indices); pass 1: wide
+        if (pass == 1) compact = false;
+        order.assign(1, 0);
+        first_child.clear();
+        for (size_t head = 0; head < order.size(); head++) {
+            const HostNode &nd = t.nodes[order[head]];
+            first_child.push_back((uint32_t)order.size());
+            if (compact) {
+                // children ordered by class; bytes without a class are handled at the root only
+                std::vector<std::pair<int, int>> ch;
+                for (auto &kv : nd.child)
+                    if (cls[kv.first] < 31) ch.push_back({cls[kv.first], kv.second});
+                std::sort(ch.begin(), ch.end());
+                for (auto &c : ch) order.push_back(c.second);
+            } else {
+                for (auto &kv : nd.child) order.push_back(kv.second);
+            }
+        }
+        n_total = order.size();
+        if (compact && n_total > 0xFFFF) continue;  // retry wide
+        break;
+    }
+
+    if (compact) {
+        words.resize(n_total * 2);
+        for (size_t i = 0; i < n_total; i++) {
+            const HostNode &nd = t.nodes[order[i]];
+            uint32_t mask = 0;
+            for (auto &kv : nd.child)
+                if (cls[kv.first] < 31) mask |= 1u << cls[kv.first];
+            uint32_t tok = nd.token >= 0 ? (uint32_t)nd.token : 0xFFFFu;
+            words[2 * i] = mask;
+            words[2 * i + 1] = (first_child[i] << 16) | tok;
+        }
+    } else {
+        words.resize(n_total * 10);
+        for (size_t i = 0; i < n_total; i++) {
+            const HostNode &nd = t.nodes[order[i]];
+            uint32_t *w = &words[10 * i];
+            std::memset(w, 0, 40);
+            for (auto &kv : nd.child) w[kv.first >> 5] |= 1u << (kv.first & 31);
+            w[8] = first_child[i];
+            w[9] = nd.token >= 0 ? (uint32_t)nd.token : 0xFFFFFFFFu;
+        }
+        for (int b = 0; b < 256; b++) cls[b] = (uint8_t)b;  // unused by the wide kernel
+    }
+
+    v->info.n_merges = n_merges;
+    v->info.n_nodes = (uint32_t)n_total;
+    v->info.n_classes = (uint32_t)n_classes;
+    v->info.compact = compact ? 1u : 0u;
+    v->info.max_token_len = t.max_len;
+    v->info.node_bytes = (uint32_t)(words.size() * 4);
+    std::memcpy(v->h_cls, cls, 256);
+    if (n_merges) {
+        v->seq.assign(h_seq, h_seq + h_seq_off[n_merges]);
+        v->seq_off.assign(h_seq_off, h_seq_off + n_merges + 1);
+        v->ids.assign(h_ids, h_ids + n_merges);
+    }
+
+    DeviceGuard g(device);
+    cudaError_t e = cudaMalloc(&v->d_nodes, words.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_cls, 256);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_nodes, words.data(), words.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_cls, cls, 256, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(v->d_nodes);
+        cudaFree(v->d_cls);
+        delete v;
+        return fail(e == cudaErrorMemoryAllocation ? ECGB_ENOMEM : ECGB_ECUDA, "vocab upload failed: %s", cudaGetErrorString(e));
+    }
+    // shared-memory residency: leave room for the quantiser tables and bookkeeping
+    int smem_max = 0;
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    size_t budget = smem_max > 24 * 1024 ? (size_t)smem_max - 16 * 1024 : 0;
+    uint32_t fit = (uint32_t)std::min<size_t>(n_total, budget / 8);
+    v->info.smem_nodes = compact ? fit : 0;
+
+    v->view.d_nodes = static_cast<const uint2 *>(v->d_nodes);
+    v->view.d_wide = static_cast<const uint32_t *>(v->d_nodes);
+    v->view.n_nodes = (uint32_t)n_total;
+    v->view.smem_nodes = v->info.smem_nodes;
+    v->view.d_cls = v->d_cls;
+    v->view.compact = compact ? 1 : 0;
+    v->view.ecg_alphabet = 1;  // classes 0..25 are always 'a'..'z' in the compact layout
+    *out = v;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_vocab_destroy(ecgb_vocab *v) {
+    if (!v) return ECGB_OK;
+    {
+        DeviceGuard g(v->device);
+        cudaFree(v->d_nodes);
+        cudaFree(v->d_cls);
+    }
+    delete v;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_vocab_info(const ecgb_vocab *v, ecgb_vocab_info_t *out) {
+    ECGB_REQUIRE(v && out, "NULL argument");
+    *out = v->info;
+    return ECGB_OK;
+}

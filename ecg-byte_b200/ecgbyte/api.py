@@ -1,0 +1,315 @@
+"""Tensor-in / tensor-out front end of libecgbyte.so.
+
+torch is used for device memory, streams and (in dist_train.py) collectives only; all
+tokenizer compute happens in the library's CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.int16: _lib.I16}
+_NP_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.int16): _lib.I16}
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _np(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_index(device):
+    if device is None:
+        _lib.require_device()
+        return torch.cuda.current_device()
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise ValueError("ecgbyte runs on CUDA devices only (got %s); there is no CPU path" % d)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+class Quantizer:
+    """normalize_all's quantiser (tokenizer_utils.py:14-19) for one stored dtype."""
+
+    def __init__(self, percentiles, dtype=torch.float32, device=None, i16_scale=1e-3):
+        if isinstance(dtype, np.dtype) or dtype in (np.float32, np.float64, np.int16):
+            dtype = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                     np.dtype(np.int16): torch.int16}[np.dtype(dtype)]
+        if dtype not in _DT:
+            raise TypeError("unsupported sample dtype %r" % (dtype,))
+        self.device = _dev_index(device)
+        self.dtype = dtype
+        self.p1 = float(percentiles["percentile_1"])
+        self.p99 = float(percentiles["percentile_99"])
+        self.i16_scale = float(i16_scale)
+        h = C.c_void_p()
+        check(lib().ecgb_quantizer_create(self.p1, self.p99, _DT[dtype], self.i16_scale, self.device, C.byref(h)))
+        self._h = h
+
+    def thresholds(self):
+        out = np.zeros(25, np.float64)
+        check(lib().ecgb_quantizer_thresholds(self._h, _np(out)))
+        return out
+
+    def _check_in(self, x):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise TypeError("expected a CUDA tensor")
+        if x.dtype != self.dtype:
+            raise TypeError("quantizer was built for %s, got %s" % (self.dtype, x.dtype))
+        if x.device.index != self.device:
+            raise ValueError("tensor on cuda:%d, quantizer on cuda:%d" % (x.device.index, self.device))
+        return x.contiguous()
+
+    def quantize(self, x, out=None, direct=False):
+        """CUDA tensor of samples -> uint8 tensor of symbols 'a'..'z' (same shape)."""
+        x = self._check_in(x)
+        if out is None:
+            out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        fn = lib().ecgb_quantize_direct if direct else lib().ecgb_quantize
+        check(fn(self._h, _ptr(x), x.numel(), _ptr(out), _stream(x.device)))
+        return out
+
+    def quantize_host(self, x):
+        """numpy array in host memory -> numpy uint8 symbols (H2D + kernel + D2H)."""
+        x = np.ascontiguousarray(x)
+        if _NP_DT.get(x.dtype) != _DT[self.dtype]:
+            raise TypeError("quantizer was built for %s, got %s" % (self.dtype, x.dtype))
+        out = np.empty(x.shape, np.uint8)
+        check(lib().ecgb_quantize_host(self._h, _np(x), x.size, _np(out)))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ecgb_quantizer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def flatten_merges(merges):
+    """list[tuple[list[int], int]] (the reference pickle form) -> flat numpy arrays."""
+    M = len(merges)
+    off = np.zeros(M + 1, np.uint64)
+    ids = np.zeros(max(M, 1), np.uint32)
+    lens = np.fromiter((len(s) for s, _ in merges), dtype=np.int64, count=M)
+    off[1:] = np.cumsum(lens)
+    for i, (_, t) in enumerate(merges):
+        ids[i] = t
+    seq = np.zeros(max(int(off[M]), 1), np.uint32)
+    k = 0
+    for s, _ in merges:
+        n = len(s)
+        seq[k: k + n] = s
+        k += n
+    return seq, off, ids
+
+
+class Vocab:
+    """A merges table flattened into a device-resident trie (lib.rs:127-161)."""
+
+    def __init__(self, merges=None, flat=None, device=None):
+        self.device = _dev_index(device)
+        seq, off, ids = flat if flat is not None else flatten_merges(merges)
+        seq = np.ascontiguousarray(seq, np.uint32)
+        off = np.ascontiguousarray(off, np.uint64)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        self.n_merges = len(off) - 1
+        h = C.c_void_p()
+        check(lib().ecgb_vocab_create(_np(seq), _np(off), _np(ids), self.n_merges, self.device, C.byref(h)))
+        self._h = h
+        self.flat = (seq, off, ids)
+
+    @classmethod
+    def from_pairs(cls, pairs, device=None):
+        seq, off = expand_merges(pairs)
+        ids = np.arange(256, 256 + len(off) - 1, dtype=np.uint32)
+        return cls(flat=(seq, off, ids), device=device)
+
+    def info(self):
+        inf = _lib.VocabInfo()
+        check(lib().ecgb_vocab_info(self._h, C.byref(inf)))
+        return {n: getattr(inf, n) for n, _ in inf._fields_}
+
+    def encode_symbols(self, sym, out_stride=None, offsets=None, tokens=None, lens=None):
+        """uint8 CUDA tensor [n_rec, rec_len] of text bytes (or flat + offsets) ->
+        (tokens int32 [n_rec, out_stride], lens int32 [n_rec])."""
+        if not (isinstance(sym, torch.Tensor) and sym.is_cuda and sym.dtype == torch.uint8):
+            raise TypeError("expected a uint8 CUDA tensor")
+        sym = sym.contiguous()
+        if offsets is not None:
+            offsets = offsets.to(device=sym.device, dtype=torch.int64).contiguous()
+            n_rec, rec_len = offsets.numel() - 1, 0
+            max_len = int((offsets[1:] - offsets[:-1]).max().item()) if n_rec else 0
+        else:
+            if sym.dim() == 1:
+                sym = sym.unsqueeze(0)
+            n_rec, rec_len = sym.shape[0], sym[0].numel() if sym.shape[0] else 0
+            max_len = rec_len
+        if out_stride is None:
+            out_stride = max(max_len, 1)
+        if tokens is None:
+            tokens = torch.empty((n_rec, out_stride), dtype=torch.int32, device=sym.device)
+        if lens is None:
+            lens = torch.empty((n_rec,), dtype=torch.int32, device=sym.device)
+        check(lib().ecgb_encode_symbols(self._h, _ptr(sym), n_rec, rec_len,
+                                        _ptr(offsets) if offsets is not None else None,
+                                        _ptr(tokens), out_stride, _ptr(lens), _stream(sym.device)))
+        return tokens, lens
+
+    def encode_batch(self, quantizer, x, out_stride=None, tokens=None, lens=None):
+        """Fused quantise + encode: CUDA tensor [n_rec, C, L] (or [n_rec, C*L]) of raw
+        samples -> (tokens int32 [n_rec, out_stride], lens int32 [n_rec])."""
+        x = quantizer._check_in(x)
+        n_rec = x.shape[0]
+        rec_len = x[0].numel() if n_rec else 0
+        if out_stride is None:
+            out_stride = max(rec_len, 1)
+        if tokens is None:
+            tokens = torch.empty((n_rec, out_stride), dtype=torch.int32, device=x.device)
+        if lens is None:
+            lens = torch.empty((n_rec,), dtype=torch.int32, device=x.device)
+        check(lib().ecgb_encode_batch(self._h, quantizer._h, _ptr(x), n_rec, rec_len, _ptr(tokens), out_stride,
+                                      _ptr(lens), _stream(x.device)))
+        return tokens, lens
+
+    def encode_batch_host(self, quantizer, x, out_stride):
+        """numpy samples in host memory -> numpy tokens / lens, copies included."""
+        x = np.ascontiguousarray(x)
+        n_rec = x.shape[0]
+        rec_len = x[0].size if n_rec else 0
+        tokens = np.empty((n_rec, out_stride), np.int32)
+        lens = np.empty((n_rec,), np.int32)
+        check(lib().ecgb_encode_batch_host(self._h, quantizer._h, _np(x), n_rec, rec_len, _np(tokens), out_stride,
+                                           _np(lens)))
+        return tokens, lens
+
+    def encode_text(self, text):
+        """One string / bytes object -> list[int] (rust_bpe.encode_text semantics)."""
+        data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+        n = len(data)
+        if n == 0:
+            return []
+        buf = np.frombuffer(data, np.uint8)
+        out = np.empty(n, np.uint32)
+        n_out = C.c_size_t(0)
+        check(lib().ecgb_encode_text_host(self._h, _np(buf), n, _np(out), n, C.byref(n_out)))
+        return out[: n_out.value].tolist()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ecgb_vocab_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def expand_merges(pairs):
+    """pairs [M, 2] -> (seq u32, off u64[M+1]): the expanded sequences (lib.rs:101-110)."""
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    M = pairs.shape[0]
+    off = np.zeros(M + 1, np.uint64)
+    rc = lib().ecgb_expand_merges(_np(pairs), M, None, 0, _np(off))
+    if rc not in (_lib.OK, _lib.ECAPACITY):
+        check(rc)
+    seq = np.zeros(max(int(off[M]), 1), np.uint32)
+    check(lib().ecgb_expand_merges(_np(pairs), M, _np(seq), seq.size, _np(off)))
+    return seq[: int(off[M])], off
+
+
+class Trainer:
+    """byte_pair_encoding (lib.rs:58-125) on one device (or one shard of a corpus)."""
+
+    def __init__(self, capacity_tokens, max_merges, device=None, table_log2=0):
+        self.device = _dev_index(device)
+        self.max_merges = int(max_merges)
+        self.capacity = int(capacity_tokens)
+        h = C.c_void_p()
+        check(lib().ecgb_trainer_create(self.device, self.capacity, self.max_merges, int(table_log2), C.byref(h)))
+        self._h = h
+
+    def load(self, text):
+        """text: bytes / numpy uint8 (host) or uint8 CUDA tensor."""
+        if isinstance(text, torch.Tensor):
+            if not (text.is_cuda and text.dtype == torch.uint8):
+                raise TypeError("expected a uint8 CUDA tensor")
+            text = text.contiguous()
+            check(lib().ecgb_trainer_load_device(self._h, _ptr(text), text.numel(), _stream(text.device)))
+            torch.cuda.current_stream(text.device).synchronize()
+            return
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        buf = np.frombuffer(bytes(text), np.uint8) if isinstance(text, (bytes, bytearray)) else \
+            np.ascontiguousarray(text, np.uint8)
+        check(lib().ecgb_trainer_load_host(self._h, _np(buf), buf.size))
+
+    def run(self, num_merges):
+        """-> (pairs u32 [m, 2], counts u64 [m], ntied u32 [m])"""
+        m = int(num_merges)
+        pairs = np.zeros((max(m, 1), 2), np.uint32)
+        counts = np.zeros(max(m, 1), np.uint64)
+        ntied = np.zeros(max(m, 1), np.uint32)
+        done = C.c_uint32(0)
+        check(lib().ecgb_trainer_run(self._h, m, _np(pairs), _np(counts), _np(ntied), C.byref(done)))
+        d = done.value
+        return pairs[:d].copy(), counts[:d].copy(), ntied[:d].copy()
+
+    def length(self):
+        n = C.c_uint64(0)
+        check(lib().ecgb_trainer_length(self._h, C.byref(n)))
+        return n.value
+
+    def ids(self):
+        n = self.length()
+        out = np.empty(max(n, 1), np.uint32)
+        got = C.c_uint64(0)
+        check(lib().ecgb_trainer_ids_host(self._h, _np(out), out.size, C.byref(got)))
+        return out[: got.value]
+
+    # ---- sharded interface (see dist_train.py) ----
+    def dist_sizes(self):
+        b, l = C.c_uint32(0), C.c_uint32(0)
+        check(lib().ecgb_trainer_dist_sizes(self._h, C.byref(b), C.byref(l)))
+        return b.value, l.value
+
+    def dist_begin(self, rank, world, boundary_out):
+        check(lib().ecgb_trainer_dist_begin(self._h, rank, world, _ptr(boundary_out), _stream(boundary_out.device)))
+
+    def dist_count(self, all_boundaries, list_out):
+        check(lib().ecgb_trainer_dist_count(self._h, _ptr(all_boundaries), _ptr(list_out), _stream(list_out.device)))
+
+    def dist_commit(self, step, all_lists, boundary_out):
+        check(lib().ecgb_trainer_dist_commit(self._h, step, _ptr(all_lists), _ptr(boundary_out),
+                                             _stream(boundary_out.device)))
+
+    def dist_merge(self, step, all_boundaries, list_out):
+        check(lib().ecgb_trainer_dist_merge(self._h, step, _ptr(all_boundaries), _ptr(list_out),
+                                            _stream(list_out.device)))
+
+    def results(self, n_steps):
+        m = int(n_steps)
+        pairs = np.zeros((max(m, 1), 2), np.uint32)
+        counts = np.zeros(max(m, 1), np.uint64)
+        ntied = np.zeros(max(m, 1), np.uint32)
+        done = C.c_uint32(0)
+        check(lib().ecgb_trainer_results(self._h, m, _np(pairs), _np(counts), _np(ntied), C.byref(done)))
+        d = done.value
+        return pairs[:d].copy(), counts[:d].copy(), ntied[:d].copy()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ecgb_trainer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

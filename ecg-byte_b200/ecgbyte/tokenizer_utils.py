@@ -1,0 +1,93 @@
+"""Mirror of the reference's ecg_byte/utils/tokenizer_utils.py for the hot path: same
+names, arguments and return values, computed by libecgbyte.so.
+
+  normalize_all, reverse_normalize_all        tokenizer_utils.py:14-28
+  process_ecg, process_large_file             tokenizer_utils.py:56-59, 79-93
+  encode_text, decode_text                    tokenizer_utils.py:71-77
+  save/load_vocab_and_merges                  tokenizer_utils.py:62-69
+"""
+import pickle
+
+import numpy as np
+import torch
+
+import rust_bpe
+from .api import Quantizer
+
+ALPHABET = list("abcdefghijklmnopqrstuvwxyz")
+_QUANT = {}
+
+
+def _quantizer(percentiles, dtype):
+    key = (float(percentiles["percentile_1"]), float(percentiles["percentile_99"]), dtype)
+    q = _QUANT.get(key)
+    if q is None:
+        q = _QUANT[key] = Quantizer(percentiles, dtype=dtype)
+    return q
+
+
+def quantize_symbols(signal, percentiles):
+    """signal (any shape; float64 / float32 / int16) -> uint8 symbol codes 'a'..'z'."""
+    x = np.ascontiguousarray(signal)
+    if x.dtype not in (np.float32, np.float64, np.int16):
+        x = x.astype(np.float64)
+    return _quantizer(percentiles, x.dtype).quantize_host(x)
+
+
+def normalize_all(signal, percentiles):
+    """-> (clipped_normalized float64 array, symbol_signal '<U1' array), tu.py:14-19."""
+    sig = np.asarray(signal)
+    codes = quantize_symbols(sig, percentiles)
+    lo = percentiles["percentile_1"] - 0.5
+    den = (percentiles["percentile_99"] + 0.5) - (percentiles["percentile_1"] - 0.5) + 1e-6
+    x = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float64)).cuda()
+    clipped = torch.clamp((x - float(lo)) / float(den), 0, 1).cpu().numpy()
+    symbol_signal = codes.view("S1").astype("<U1").reshape(sig.shape)
+    return clipped, symbol_signal
+
+
+def reverse_normalize_all(symbol_signal, percentiles):
+    """tu.py:22-28 (note: divides by len(ALPHABET) - 1 = 25, as the reference does)."""
+    min_vals = percentiles["percentile_1"] - 0.5
+    max_vals = percentiles["percentile_99"] + 0.5
+    arr = np.asarray(symbol_signal)
+    codes = arr.astype("S1").view(np.uint8).reshape(arr.shape).astype(np.float64) - 97.0
+    return codes / (len(ALPHABET) - 1) * (max_vals - min_vals) + min_vals
+
+
+def process_ecg(ecg, percentiles):
+    """path of a (C, L) .npy record -> its symbol string, lead-major (tu.py:56-59)."""
+    sig = np.load(ecg) if isinstance(ecg, (str, bytes)) else np.asarray(ecg)
+    return quantize_symbols(sig, percentiles).tobytes().decode("ascii")
+
+
+def process_large_file(file_path, percentiles, num_processes=None, n=None):
+    """tu.py:79-93: every listed record quantised and joined into ONE string, in file
+    order.  `num_processes` is accepted for compatibility (the GPU path needs no pool)."""
+    paths = []
+    with open(file_path, "r") as f:
+        for i, line in enumerate(f):
+            if n is not None and i >= n:
+                break
+            paths.append(line.strip())
+    parts = [process_ecg(p, percentiles) for p in paths]
+    return "".join(parts)
+
+
+def save_vocab_and_merges(vocab, merges, filename):
+    with open(filename, "wb") as f:
+        pickle.dump((vocab, merges), f)
+
+
+def load_vocab_and_merges(filename):
+    with open(filename, "rb") as f:
+        vocab, merges = pickle.load(f)
+    return vocab, merges
+
+
+def encode_text(text, merges):
+    return rust_bpe.encode_text(text, merges)
+
+
+def decode_text(encoded_ids, vocab):
+    return "".join(vocab[i] for i in encoded_ids)

@@ -1,0 +1,201 @@
+/*
+ * ecgbyte.h -- C ABI of libecgbyte.so, the B200 (sm_100a) implementation of the
+ * ECG-Byte tokenizer hot path.
+ *
+ * This is the drop-in boundary for the reference's only native component, the
+ * PyO3 module `rust_bpe` (/root/reference/ecg_byte/rust_bpe/src/lib.rs:195-199)
+ * and for the quantiser in front of it (ecg_byte/utils/tokenizer_utils.py:14-19).
+ * Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures.
+ *     `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - pointers named d_* are DEVICE pointers on the handle's device, h_* are HOST
+ *     pointers.  The library never frees caller memory.
+ *   - every function returns an ecgb_status; ecgb_last_error() gives the message
+ *     of the last failure on the calling thread.  Nothing throws or aborts across
+ *     the ABI (the reference panics through .unwrap(), lib.rs:68,81,106-107).
+ *   - handles are thread-compatible: distinct handles / streams may be used from
+ *     distinct threads concurrently.  There is no global mutable state.
+ *   - launches are asynchronous on `stream` unless the name ends in _host.
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     ECGB_ENODEVICE when no CUDA device is usable.
+ */
+#ifndef ECGBYTE_H
+#define ECGBYTE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ECGB_OK = 0,
+    ECGB_EINVAL = 1,    /* bad argument (message says which) */
+    ECGB_ENOMEM = 2,    /* host or device allocation failed */
+    ECGB_ECUDA = 3,     /* CUDA runtime error (message carries cudaGetErrorString) */
+    ECGB_ENODEVICE = 4, /* no usable CUDA device */
+    ECGB_ECAPACITY = 5, /* an output buffer / table capacity was too small */
+    ECGB_EUNSUPPORTED = 6
+} ecgb_status;
+
+/* stored sample types of a record (float64 is the reference's
+ * on-disk type, preprocess_utils.py:94,220-223; fp32 / int16 are the compact
+ * variants named by BASELINE.json).  ECGB_U8 = already-quantised text bytes. */
+typedef enum { ECGB_F32 = 0, ECGB_F64 = 1, ECGB_I16 = 2, ECGB_U8 = 3 } ecgb_dtype;
+
+typedef struct ecgb_quantizer ecgb_quantizer;
+typedef struct ecgb_vocab ecgb_vocab;
+typedef struct ecgb_trainer ecgb_trainer;
+
+const char *ecgb_last_error(void);
+int ecgb_version(void);
+/* number of CUDA devices visible (0 and ECGB_ENODEVICE when there is none) */
+int ecgb_device_count(int *n_out);
+
+/* ------------------------------------------------------------------------- */
+/* Q1  normalize_all  (tokenizer_utils.py:14-19; ALPHABET tokenizer_utils.py:12) */
+/* ------------------------------------------------------------------------- */
+/* symbol = 'a' + min(floor(clip((s - (p1-0.5)) / ((p99+0.5)-(p1-0.5)+1e-6), 0, 1) * 26), 25),
+ * evaluated in float64 in exactly that order.  The expression is a non-decreasing
+ * step function of s, so it is fully described by 25 thresholds t_k = the smallest
+ * representable sample with symbol >= k; the quantiser object holds them (found by
+ * bisection with the float64 expression itself) and the kernels classify against
+ * them -- bit-identical to the expression, without a float64 divide per sample.
+ * int16 samples are de-scaled first: s = (double)v * i16_scale.
+ * NaN -> 'a' (NumPy's NaN->uint8 cast on x86-64). Fails with ECGB_EINVAL when the
+ * denominator is not > 0 or a percentile is not finite. */
+int ecgb_quantizer_create(double p1, double p99, ecgb_dtype dtype, double i16_scale, int device,
+                          ecgb_quantizer **out);
+int ecgb_quantizer_destroy(ecgb_quantizer *q);
+/* the 25 thresholds as doubles (every stored type converts to double exactly) */
+int ecgb_quantizer_thresholds(const ecgb_quantizer *q, double h_thr_out[25]);
+/* d_in: n samples of the quantiser's dtype -> d_out: n bytes 'a'..'z' */
+int ecgb_quantize(const ecgb_quantizer *q, const void *d_in, size_t n, uint8_t *d_out, void *stream);
+/* same result computed sample by sample with the float64 expression on the device
+ * (reference operation order, IEEE divide, no FMA) -- the on-device cross-check */
+int ecgb_quantize_direct(const ecgb_quantizer *q, const void *d_in, size_t n, uint8_t *d_out,
+                         void *stream);
+/* host buffers in/out (H2D, kernel, D2H, synchronous) */
+int ecgb_quantize_host(const ecgb_quantizer *q, const void *h_in, size_t n, uint8_t *h_out);
+
+/* ------------------------------------------------------------------------- */
+/* E1  TrieNode / trie build  (lib.rs:127-147, 153-161)                      */
+/* ------------------------------------------------------------------------- */
+/* merges in the reference's pickle form, flattened: merge i has the expanded
+ * base-symbol sequence seq[seq_off[i] .. seq_off[i+1]) and token id ids[i]
+ * (list[tuple[list[int], int]], lib.rs:110,150).  All 256 single bytes are
+ * inserted first (lib.rs:155-157); a later duplicate sequence overwrites the
+ * token id (lib.rs:145).  The trie is flattened once and kept resident on
+ * `device` (the reference rebuilds it on every encode call). */
+int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_off, const uint32_t *h_ids,
+                      uint32_t n_merges, int device, ecgb_vocab **out);
+int ecgb_vocab_destroy(ecgb_vocab *v);
+
+typedef struct {
+    uint32_t n_merges;
+    uint32_t n_nodes;       /* trie nodes incl. root */
+    uint32_t n_classes;     /* distinct symbols that occur inside merges (+ a..z) */
+    uint32_t compact;       /* 1: 8-byte bitmap nodes (<= 31 classes), 0: wide nodes */
+    uint32_t max_token_len; /* longest expanded sequence */
+    uint32_t node_bytes;    /* size of the device node table */
+    uint32_t smem_nodes;    /* nodes the encode kernel keeps in shared memory */
+    uint32_t reserved;
+} ecgb_vocab_info_t;
+int ecgb_vocab_info(const ecgb_vocab *v, ecgb_vocab_info_t *out);
+
+/* ------------------------------------------------------------------------- */
+/* E2  encode_text  (lib.rs:149-193) -- greedy longest match over the trie    */
+/* ------------------------------------------------------------------------- */
+/* Batch of records of text bytes.  Record r is d_sym[off[r] .. off[r+1]) when
+ * d_offsets != NULL (n_rec+1 entries), else d_sym[r*rec_len .. (r+1)*rec_len).
+ * Tokens of record r go to d_tokens[r*out_stride ..]; d_len[r] is the TRUE token
+ * count (tokens beyond out_stride are counted but not stored). */
+int ecgb_encode_symbols(const ecgb_vocab *v, const uint8_t *d_sym, size_t n_rec, size_t rec_len,
+                        const uint64_t *d_offsets, int32_t *d_tokens, size_t out_stride,
+                        int32_t *d_len, void *stream);
+/* Fused Q1+E2 (data_loader.py:74-76): raw samples -> token ids; record r is the
+ * rec_len = C*L samples at d_in + r*rec_len, lead-major (C-order flatten,
+ * tokenizer_utils.py:59).  Symbols never touch HBM.  The vocabulary must map
+ * 'a'..'z' (every ECG-Byte vocabulary does). */
+int ecgb_encode_batch(const ecgb_vocab *v, const ecgb_quantizer *q, const void *d_in, size_t n_rec,
+                      size_t rec_len, int32_t *d_tokens, size_t out_stride, int32_t *d_len,
+                      void *stream);
+/* rust_bpe.encode_text(text, merges) for one string with host buffers: returns
+ * the token count in *n_out; ECGB_ECAPACITY (with *n_out set) when cap is too small. */
+int ecgb_encode_text_host(const ecgb_vocab *v, const uint8_t *h_text, size_t n, uint32_t *h_out,
+                          size_t cap, size_t *n_out);
+/* Same as ecgb_encode_batch with HOST sample / token buffers (pinned or pageable):
+ * H2D copy, kernel, D2H copy of tokens and lengths, synchronous. */
+int ecgb_encode_batch_host(const ecgb_vocab *v, const ecgb_quantizer *q, const void *h_in,
+                           size_t n_rec, size_t rec_len, int32_t *h_tokens, size_t out_stride,
+                           int32_t *h_len);
+
+/* ------------------------------------------------------------------------- */
+/* T1-T4  byte_pair_encoding  (lib.rs:58-125)                                */
+/* ------------------------------------------------------------------------- */
+/* The corpus is ONE string (tokenizer_utils.py:93): pairs are counted and merged
+ * across record boundaries.  A trainer owns a contiguous shard of that string
+ * (the whole string when world_size == 1).
+ *
+ * Tie rule (the reference's winner depends on hash-map iteration order,
+ * lib.rs:92-94): maximum count, then the lexicographically smallest (left,right).
+ * Counts are 64-bit (the reference's u32 counts wrap). */
+/* table_log2: log2 of the pair-histogram capacity in slots (0 = default 2^22); the
+ * run fails with ECGB_ECAPACITY (never silently) if the distinct pairs outgrow it. */
+int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_t max_merges, uint32_t table_log2,
+                        ecgb_trainer **out);
+int ecgb_trainer_destroy(ecgb_trainer *t);
+/* load this rank's shard: n bytes of text (device or host pointer) */
+int ecgb_trainer_load_device(ecgb_trainer *t, const uint8_t *d_text, uint64_t n, void *stream);
+int ecgb_trainer_load_host(ecgb_trainer *t, const uint8_t *h_text, uint64_t n);
+/* Single-device training loop: runs up to num_merges merge steps entirely on the
+ * device (count -> argmax -> merge-apply, lib.rs:85-117) and returns the number
+ * done (early stop when no pair is left, lib.rs:88-90).
+ * h_pairs[2*i], h_pairs[2*i+1] = (left,right) of merge i (new id 256+i);
+ * h_counts[i] = its count; h_ntied[i] = number of pairs sharing that count. */
+int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *h_pairs, uint64_t *h_counts,
+                     uint32_t *h_ntied, uint32_t *n_done);
+/* current length of the merged token stream, and a copy of it (lib.rs:124 `ids`) */
+int ecgb_trainer_length(ecgb_trainer *t, uint64_t *n_out);
+int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t cap, uint64_t *n_out);
+
+/* Step-wise interface for a corpus sharded over ranks (one trainer per rank holds a
+ * CONTIGUOUS piece of the one corpus string, in rank order).  All calls
+ * are asynchronous on `stream`; the two exchanges per step are plain all-gathers of
+ * fixed-size device buffers done by the host (torch.distributed / NCCL):
+ *
+ *   dist_begin(rank, world)            -> boundary record            | all-gather
+ *   dist_count(all boundaries)         -> delta list (local get_stats)| all-gather
+ *   for step in 0..M:
+ *     dist_commit(step, all lists)     -> applies every rank's list to the local copy
+ *                                         of the GLOBAL histogram, argmax (identical on
+ *                                         every rank), boundary record | all-gather
+ *     dist_merge(step, all boundaries) -> merges in this shard (halo tokens and run
+ *                                         parity come from the records), delta list
+ *                                                                     | all-gather
+ *   results()                          -> merges, counts, tie log
+ *
+ * Every rank applies the same lists in the same order, so the histograms -- and the
+ * argmax -- are identical without any reduction. */
+int ecgb_trainer_dist_sizes(const ecgb_trainer *t, uint32_t *boundary_bytes, uint32_t *list_bytes);
+int ecgb_trainer_dist_begin(ecgb_trainer *t, int rank, int world, void *d_boundary_out, void *stream);
+int ecgb_trainer_dist_count(ecgb_trainer *t, const void *d_all_boundaries, void *d_list_out, void *stream);
+int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const void *d_all_lists, void *d_boundary_out,
+                             void *stream);
+int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const void *d_all_boundaries, void *d_list_out,
+                            void *stream);
+int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t *h_pairs, uint64_t *h_counts,
+                         uint32_t *h_ntied, uint32_t *n_done);
+
+/* expanded sequences of merges given as pairs (lib.rs:101-110); two-call sizing:
+ * h_seq_off[n_merges] always receives the total length. */
+int ecgb_expand_merges(const uint32_t *h_pairs, uint32_t n_merges, uint32_t *h_seq, uint64_t seq_cap,
+                       uint64_t *h_seq_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECGBYTE_H */

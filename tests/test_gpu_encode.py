@@ -1,0 +1,115 @@
+"""K2 parity: CUDA greedy longest-match encoder vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _check_batch(oracle, vocab, trie, sym):
+    want_tok, want_len = trie.encode_batch(sym)
+    tok, lens = vocab.encode_symbols(torch.from_numpy(sym).cuda())
+    tok, lens = tok.cpu().numpy(), lens.cpu().numpy()
+    np.testing.assert_array_equal(lens, want_len.astype(np.int32))
+    for r in range(sym.shape[0]):
+        np.testing.assert_array_equal(tok[r, : lens[r]], want_tok[r, : want_len[r]].astype(np.int32))
+
+
+def test_encode_symbols_matches_oracle(oracle, small_corpus, small_table):
+    from ecgbyte.api import Vocab
+    x, pct = small_corpus
+    _, _, merges = small_table
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(x.shape[0], -1)
+    v = Vocab(merges=merges)
+    info = v.info()
+    assert info["compact"] == 1 and info["n_merges"] == len(merges)
+    trie = oracle.Trie(merges=merges)
+    assert info["n_nodes"] == trie.nodes - (256 - 26)  # bytes outside a..z stay implicit
+    _check_batch(oracle, v, trie, sym)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "int16"])
+def test_fused_encode_matches_oracle(oracle, small_corpus, small_table, dtype):
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Vocab
+    x64, pct = small_corpus
+    _, _, merges = small_table
+    x = synth.cast(x64, np.dtype(dtype))
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(x.shape[0], -1)
+    trie = oracle.Trie(merges=merges)
+    want_tok, want_len = trie.encode_batch(sym)
+    v = Vocab(merges=merges)
+    q = Quantizer(pct, dtype=getattr(torch, dtype))
+    tok, lens = v.encode_batch(q, torch.from_numpy(x).cuda())
+    tok, lens = tok.cpu().numpy(), lens.cpu().numpy()
+    np.testing.assert_array_equal(lens, want_len.astype(np.int32))
+    for r in range(x.shape[0]):
+        np.testing.assert_array_equal(tok[r, : lens[r]], want_tok[r, : want_len[r]].astype(np.int32))
+    # host-buffer entry point, truncated output: lengths stay true, stored prefix matches
+    tok_h, len_h = v.encode_batch_host(q, x, 64)
+    np.testing.assert_array_equal(len_h, want_len.astype(np.int32))
+    for r in range(x.shape[0]):
+        m = min(64, want_len[r])
+        np.testing.assert_array_equal(tok_h[r, :m], want_tok[r, :m].astype(np.int32))
+
+
+def test_encode_kats():
+    """Hand-derived known answers."""
+    import rust_bpe
+    # longest match, not merge order: 'abc' with [bc->256, ab->257] -> [257, 'c']
+    assert rust_bpe.encode_text("abc", [([98, 99], 256), ([97, 98], 257)]) == [257, 99]
+    # a duplicate sequence: the later id wins (lib.rs:145)
+    assert rust_bpe.encode_text("abab", [([97, 98], 256), ([97, 98], 300)]) == [300, 300]
+    # non-terminal interior node: 'aaaa' is a token, 'aaa' is not
+    m = [([97, 97], 256), ([97, 97, 97, 97], 257)]
+    assert rust_bpe.encode_text("aaa", m) == [256, 97]
+    assert rust_bpe.encode_text("aaaaa", m) == [257, 97]
+    assert rust_bpe.encode_text("", m) == []
+    # bytes that occur in no merge, and non-ASCII text (UTF-8 bytes, lib.rs:151)
+    assert rust_bpe.encode_text("a-b", m) == [97, 45, 98]
+    assert rust_bpe.encode_text("é", []) == [0xC3, 0xA9]
+    with pytest.raises(TypeError):
+        rust_bpe.encode_text(b"abc", m)
+    with pytest.raises(TypeError):
+        rust_bpe.encode_text("abc", "nope")
+
+
+def test_encode_ragged_and_edge_records(oracle, small_table):
+    from ecgbyte.api import Vocab
+    _, _, merges = small_table
+    v = Vocab(merges=merges)
+    trie = oracle.Trie(merges=merges)
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 7, 8, 9, 15, 16, 17, 33, 1000, 0, 4099]
+    parts = [rng.integers(97, 123, size=n).astype(np.uint8) for n in lens]
+    # long runs and a constant record exercise deep walks and long reach-backs
+    parts[10][:] = 105
+    parts[12][:2000] = 104
+    flat = np.concatenate(parts + [np.zeros(1, np.uint8)])[:-1]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok, ln = v.encode_symbols(torch.from_numpy(flat).cuda(), offsets=torch.from_numpy(off))
+    tok, ln = tok.cpu().numpy(), ln.cpu().numpy()
+    for r, p in enumerate(parts):
+        want = trie.encode(p)
+        assert ln[r] == len(want)
+        np.testing.assert_array_equal(tok[r, : ln[r]], want.astype(np.int32))
+
+
+def test_encode_wide_alphabet(oracle):
+    """> 31 symbol classes -> wide-node kernel (general text)."""
+    import rust_bpe
+    text = "".join(chr(33 + (i * 7 + (i // 5) * 3) % 60) for i in range(4000)) * 2
+    ids, vocab, merges = oracle.byte_pair_encoding(text, 200, fast=True)
+    from ecgbyte.api import Vocab
+    assert Vocab(merges=merges).info()["compact"] == 0
+    assert rust_bpe.encode_text(text, merges) == oracle.encode_text(text, merges)
+
+
+def test_roundtrip_decode(oracle, small_corpus, small_table):
+    from ecgbyte import tokenizer_utils as tu
+    x, pct = small_corpus
+    _, vocab, merges = small_table
+    s = tu.process_ecg(x[3], pct)
+    ids = tu.encode_text(s, merges)
+    assert tu.decode_text(ids, vocab) == s  # train_tokenizer.py:58-60
+    assert ids == oracle.encode_text(s, merges)
