@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
         // (a != b, first token of the shard): e[1] is the left halo, handled by the general rule.
 
         // ---- histogram patches at the sites (see oracle/ecgb_oracle.c ecgo_train_fast) ----
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < kIPT; i++) {
             const bool st = (site >> i) & 1u;
             if (!__any_sync(0xffffffffu, st)) continue;
@@ -801,6 +801,33 @@ extern "C" int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t 
         ECGB_CUDA(cudaGetLastError());
         ECGB_CUDA(cudaMemcpy(h_ids + o, d_tmp, c * 4, cudaMemcpyDeviceToHost));
     }
+    return ECGB_OK;
+}
+
+// The live pair histogram (every pair with a non-zero count): get_stats (lib.rs:28-48)
+// of the current token stream.  Used by the parity tests.
+extern "C" int ecgb_trainer_histogram(ecgb_trainer *t, uint32_t *h_pairs, int64_t *h_counts, uint64_t cap,
+                                      uint64_t *n_out) {
+    ECGB_REQUIRE(t && n_out, "NULL argument");
+    DeviceGuard g(t->device);
+    ECGB_CUDA(cudaDeviceSynchronize());
+    const size_t slots = (size_t)t->v.main.mask + 1;
+    std::vector<uint32_t> keys(slots);
+    std::vector<unsigned long long> cnt(slots);
+    ECGB_CUDA(cudaMemcpy(keys.data(), t->v.main.keys, slots * 4, cudaMemcpyDeviceToHost));
+    ECGB_CUDA(cudaMemcpy(cnt.data(), t->v.main.cnt, slots * 8, cudaMemcpyDeviceToHost));
+    uint64_t k = 0;
+    for (size_t i = 0; i < slots; i++) {
+        if (keys[i] == kEmptyKey || cnt[i] == 0) continue;
+        if (k < cap && h_pairs && h_counts) {
+            h_pairs[2 * k] = keys[i] >> 16;
+            h_pairs[2 * k + 1] = keys[i] & 0xFFFFu;
+            h_counts[k] = (int64_t)cnt[i];
+        }
+        k++;
+    }
+    *n_out = k;
+    if (k > cap) return fail(ECGB_ECAPACITY, "histogram has %llu entries", (unsigned long long)k);
     return ECGB_OK;
 }
 

@@ -276,6 +276,17 @@ class Trainer:
         check(lib().ecgb_trainer_ids_host(self._h, _np(out), out.size, C.byref(got)))
         return out[: got.value]
 
+    def histogram(self):
+        """{(left, right): count} of the live pair histogram."""
+        n = C.c_uint64(0)
+        rc = lib().ecgb_trainer_histogram(self._h, None, None, 0, C.byref(n))
+        if rc not in (_lib.OK, _lib.ECAPACITY):
+            check(rc)
+        pairs = np.zeros((max(n.value, 1), 2), np.uint32)
+        counts = np.zeros(max(n.value, 1), np.int64)
+        check(lib().ecgb_trainer_histogram(self._h, _np(pairs), _np(counts), pairs.shape[0], C.byref(n)))
+        return {(int(l), int(r)): int(c) for (l, r), c in zip(pairs[: n.value].tolist(), counts[: n.value].tolist())}
+
     # ---- sharded interface (see dist_train.py) ----
     def dist_sizes(self):
         b, l = C.c_uint32(0), C.c_uint32(0)

@@ -41,7 +41,9 @@ def normalize_all(signal, percentiles):
     lo = percentiles["percentile_1"] - 0.5
     den = (percentiles["percentile_99"] + 0.5) - (percentiles["percentile_1"] - 0.5) + 1e-6
     x = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float64)).cuda()
-    clipped = torch.clamp((x - float(lo)) / float(den), 0, 1).cpu().numpy()
+    # tensor / tensor is an IEEE divide (tensor / python-scalar multiplies by a reciprocal)
+    den_t = torch.tensor([float(den)], dtype=torch.float64, device=x.device)
+    clipped = torch.clamp((x - float(lo)) / den_t, 0, 1).cpu().numpy()
     symbol_signal = codes.view("S1").astype("<U1").reshape(sig.shape)
     return clipped, symbol_signal
 
