@@ -214,6 +214,44 @@ class Vocab:
             pass
 
 
+class EncodePipeline:
+    """Host-buffer front end of the fused encoder: records in PINNED host memory ->
+    tokens / lengths in pinned host memory.  Chunks are double-buffered over CUDA streams
+    so the H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1
+    overlap (the path is PCIe-bound: 240 KB in per fp32 record)."""
+
+    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
+        self.vocab, self.q = vocab, quantizer
+        self.rec_len, self.out_stride, self.chunk, self.depth = rec_len, out_stride, chunk, depth
+        dev = torch.device("cuda", vocab.device)
+        self.dev = dev
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.d_in = [torch.empty((chunk, rec_len), dtype=quantizer.dtype, device=dev) for _ in range(depth)]
+        self.d_tok = [torch.empty((chunk, out_stride), dtype=torch.int32, device=dev) for _ in range(depth)]
+        self.d_len = [torch.empty((chunk,), dtype=torch.int32, device=dev) for _ in range(depth)]
+
+    def run(self, x_pinned, tokens_pinned, lens_pinned):
+        n = x_pinned.shape[0]
+        x2 = x_pinned.view(n, self.rec_len)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        k = 0
+        for c0 in range(0, n, self.chunk):
+            m = min(self.chunk, n - c0)
+            b = k % self.depth
+            k += 1
+            with torch.cuda.stream(self.streams[b]):
+                self.d_in[b][:m].copy_(x2[c0:c0 + m], non_blocking=True)
+                self.vocab.encode_batch(self.q, self.d_in[b][:m], out_stride=self.out_stride,
+                                        tokens=self.d_tok[b], lens=self.d_len[b])
+                tokens_pinned[c0:c0 + m].copy_(self.d_tok[b][:m], non_blocking=True)
+                lens_pinned[c0:c0 + m].copy_(self.d_len[b][:m], non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return k  # kernel launches
+
+
 def expand_merges(pairs):
     """pairs [M, 2] -> (seq u32, off u64[M+1]): the expanded sequences (lib.rs:101-110)."""
     pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)

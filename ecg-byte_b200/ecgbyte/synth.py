@@ -62,4 +62,34 @@ def percentiles(records_mv, sample_size=100000, seed=0):
 
 # Fixed stats for the benchmark corpora (computed once from corpus(seed=0, n=1000);
 # kept literal so every rank / run quantises identically without a data pass).
-BENCH_PERCENTILES = {"percentile_1": np.float64(-0.18755), "percentile_99": np.float64(0.79872)}
+BENCH_PERCENTILES = {"percentile_1": np.float64(-0.1610814356803894), "percentile_99": np.float64(0.9105487620830528)}
+
+
+def corpus_cuda(seed, n, L=5000, dtype=None, device=None, start=0, chunk=2048):
+    """Same distribution as corpus(), generated on the device with torch (bulk benchmark
+    data: 100k records = 24 GB would take minutes in NumPy).  Record streams are not
+    bit-identical to record(); parity checks read the generated tensors back."""
+    import torch
+    dtype = dtype or torch.float32
+    device = torch.device(device if device is not None else "cuda")
+    out = torch.empty((n, N_LEADS, L), dtype=dtype, device=device)
+    t = torch.arange(L, dtype=torch.float32, device=device) / FS
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        g = torch.Generator(device=device)
+        g.manual_seed((int(seed) << 32) + start + c0)
+        hr = torch.empty((m, 1, 1), device=device).uniform_(50.0, 110.0, generator=g)
+        ph = torch.empty((m, 1, 1), device=device).uniform_(0.0, 1.0, generator=g)
+        amp = torch.empty((m, N_LEADS, 1), device=device).normal_(1.0, 0.4, generator=g)
+        wphi = torch.empty((m, N_LEADS, 1), device=device).uniform_(0.0, 6.283185307, generator=g)
+        beat = torch.remainder(t.view(1, 1, L) * (hr / 60.0) + ph, 1.0)
+        x = torch.zeros((m, N_LEADS, L), device=device)
+        for a, c, s in _WAVES:
+            x += (a * amp) * torch.exp(-0.5 * ((beat - c) / s) ** 2)
+        x += 0.05 * torch.sin(6.283185307 * 0.3 * t.view(1, 1, L) + wphi)
+        x += torch.empty((m, N_LEADS, L), device=device).normal_(0.0, 0.01, generator=g)
+        if dtype == torch.int16:
+            out[c0:c0 + m] = torch.clamp(torch.round(x * 1000.0), -32768, 32767).to(torch.int16)
+        else:
+            out[c0:c0 + m] = x.to(dtype)
+    return out

@@ -89,3 +89,34 @@ def test_byte_pair_encoding_reference_types(oracle, small_corpus):
     assert isinstance(merges[0], tuple) and isinstance(merges[0][0], list) and isinstance(merges[0][1], int)
     assert (ids, vocab, merges) == o
     assert len(vocab) == 256 + len(merges)
+
+
+def test_train_config1_scale_matches_fixture():
+    """BASELINE.json config 1: 1,000 PTB-XL-shaped records (6e7 symbols), 5,000 merges.
+    The expected merge list / counts / tie log / final stream come from the oracle
+    (tests/golden/ptbxl_1000_m5000.npz, oracle/make_table_fixture.py)."""
+    import os
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Trainer
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptbxl_1000_m5000.npz"))
+    x = synth.corpus(0, 1000, 5000, np.float32)
+    pct = synth.percentiles(x, seed=0)
+    assert [pct["percentile_1"], pct["percentile_99"]] == f["pct"].tolist()
+    q = Quantizer(pct, dtype=torch.float32)
+    sym = q.quantize(torch.from_numpy(x).cuda()).reshape(-1)
+    tr = Trainer(sym.numel(), 5000)
+    tr.load(sym)
+    pairs, counts, ntied = tr.run(5000)
+    np.testing.assert_array_equal(pairs, f["pairs"].astype(np.uint32))
+    np.testing.assert_array_equal(counts, f["counts"])
+    np.testing.assert_array_equal(ntied, f["ntied"])
+    ids = tr.ids()
+    assert len(ids) == int(f["n_ids"][0])
+    crc = np.bitwise_xor.reduce(ids.astype(np.uint64) * (np.arange(len(ids), dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)))
+    assert int(crc) == int(f["ids_crc"][0])
+    # the live histogram equals a recount of the final stream (get_stats, lib.rs:28-48)
+    h = tr.histogram()
+    keys = (ids[:-1].astype(np.uint64) << np.uint64(32)) | ids[1:].astype(np.uint64)
+    uk, uc = np.unique(keys, return_counts=True)
+    want = {(int(k >> np.uint64(32)), int(k & np.uint64(0xFFFFFFFF))): int(c) for k, c in zip(uk, uc)}
+    assert h == want
