@@ -44,62 +44,60 @@ struct EncArgs {
 constexpr uint32_t kNoTok = 0xFFFFu;
 constexpr uint32_t kNoClass = 31u;
 
-// ---- 8-sample groups: the unit a walker loads, quantises and slides by ----
-template <int DT> struct RawGroup;
-template <> struct RawGroup<ECGB_F32> { uint4 v[2]; };
-template <> struct RawGroup<ECGB_F64> { uint4 v[4]; };
-template <> struct RawGroup<ECGB_I16> { uint4 v[1]; };
-template <> struct RawGroup<ECGB_U8>  { uint2 v[1]; };
-
+// ---- 16-sample groups: the unit a walker loads, quantises and appends to its ring ----
 template <int DT> struct ElemOf { using T = typename SampleTraits<DT>::In; };
 template <> struct ElemOf<ECGB_U8> { using T = uint8_t; };
+template <int DT> struct ThrOf { using T = typename SampleTraits<DT>::Thr; };
+template <> struct ThrOf<ECGB_U8> { using T = float; };
 
-template <int DT>
-__device__ __forceinline__ void load_group(RawGroup<DT> &r, const void *base, size_t g, size_t n_total) {
+constexpr int kRing = 64;         // symbols a walker keeps in shared memory
+constexpr int kRingStride = 80;   // bytes between rings: 16-byte stores of 8 lanes hit 8 distinct bank groups
+constexpr int kGroup = 16;
+
+// 16 samples at global index g (g % 16 == 0) -> 16 symbol classes, one per byte.
+template <int DT, bool CELLS>
+__device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_total, const void *qsmem,
+                                         const void *thr_smem, float lo, float scale) {
     using T = typename ElemOf<DT>::T;
     const T *p = static_cast<const T *>(base) + g;
-    if (g + 8 <= n_total) {
-        if constexpr (DT == ECGB_U8) {
-            r.v[0] = __ldg(reinterpret_cast<const uint2 *>(p));
-        } else {
-            constexpr int NV = sizeof(T) * 8 / 16;
+    constexpr int NV = sizeof(T);  // 16-byte vectors per group
+    uint4 raw[NV];
+    if (g + kGroup <= n_total) {
 #pragma unroll
-            for (int j = 0; j < NV; j++) r.v[j] = __ldg(reinterpret_cast<const uint4 *>(p) + j);
-        }
+        for (int j = 0; j < NV; j++) raw[j] = __ldg(reinterpret_cast<const uint4 *>(p) + j);
     } else {  // ragged end of the buffer: element-wise, zero filled
-        T tmp[8];
+        T tmp[kGroup];
 #pragma unroll
-        for (int k = 0; k < 8; k++) tmp[k] = (g + k < n_total) ? p[k] : T(0);
-        memcpy(&r, tmp, sizeof(r));
+        for (int k = 0; k < kGroup; k++) tmp[k] = (g + k < n_total) ? p[k] : T(0);
+        memcpy(raw, tmp, sizeof(raw));
     }
-}
-
-// 8 samples -> 8 symbol classes packed one per byte (x = samples 0..3, y = 4..7).
-template <int DT, bool CELLS>
-__device__ __forceinline__ uint2 quantize_group(const RawGroup<DT> &r, const void *qsmem, const void *thr_smem,
-                                                float lo, float scale) {
     if constexpr (DT == ECGB_U8) {
-        return r.v[0];  // text bytes; class lookup happens per step
+        return raw[0];  // text bytes; the class lookup happens per step
     } else {
-        using T = typename SampleTraits<DT>::In;
         using Thr = typename SampleTraits<DT>::Thr;
-        const T *e = reinterpret_cast<const T *>(&r);
-        uint32_t w[2] = {0, 0};
+        const T *e = reinterpret_cast<const T *>(raw);
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < kGroup; k++) {
             float sf;
             Thr s = to_thr(e[k], &sf);
             uint32_t q = CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
                                : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
             w[k >> 2] |= q << ((k & 3) * 8);
         }
-        return make_uint2(w[0], w[1]);
+        return make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
-template <int DT> struct ThrOf { using T = typename SampleTraits<DT>::Thr; };
-template <> struct ThrOf<ECGB_U8> { using T = float; };
-
+// One walker (thread) per record.  A warp alternates between two CONVERGENT phases so
+// that the 32 walkers never serialise on each other's bookkeeping:
+//   refill: every lane with room appends up to four 16-sample groups to its private ring
+//           (128-bit loads -> threshold classification -> one STS.128 per group); lanes
+//           that finished a record pick up their next one here;
+//   walk:   pure trie steps (one LDS.U8 symbol + one LDS.64 node per step) until some
+//           lane runs out of symbols or finishes its record.
+// All lanes consume ~1 symbol per step, so their rings drain in lockstep and nearly all
+// lanes take part in every refill.
 template <int DT, bool CELLS>
 __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     using Thr = typename ThrOf<DT>::T;
@@ -111,6 +109,8 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     QuantSmem<Thr> *qs = reinterpret_cast<QuantSmem<Thr> *>(s_aux);
     Thr *s_thr = reinterpret_cast<Thr *>(s_aux + sizeof(QuantSmem<Thr>));
     uint8_t *s_cls = s_aux;
+    constexpr size_t kAux = DT == ECGB_U8 ? 256 : sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32;
+    uint8_t *ring = s_aux + kAux + (size_t)threadIdx.x * kRingStride;
 
     for (uint32_t i = threadIdx.x; i < a.smem_nodes; i += blockDim.x) s_nodes[i] = a.nodes[i];
     if constexpr (DT == ECGB_U8) {
@@ -125,78 +125,101 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     const uint32_t S = a.smem_nodes;
     // explicit offsets: the buffer ends where the last record ends
     const size_t n_total = a.offsets ? (size_t)a.offsets[a.n_rec] : a.n_total;
-    const uint2 root = s_nodes[0];
-    const uint32_t root_mask = root.x, root_base = root.y >> 16;
+    constexpr unsigned FULL = 0xffffffffu;
 
     // contiguous, even split of the records over the CTAs
     const size_t r_lo = (size_t)(((unsigned __int128)a.n_rec * blockIdx.x) / gridDim.x);
     const size_t r_hi = (size_t)(((unsigned __int128)a.n_rec * (blockIdx.x + 1)) / gridDim.x);
+    size_t r_next = r_lo + threadIdx.x;
 
-    for (size_t r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
-        const size_t rs = a.offsets ? (size_t)a.offsets[r] : r * a.rec_len;
-        const size_t re = a.offsets ? (size_t)a.offsets[r + 1] : rs + a.rec_len;
-        int32_t *outp = a.tokens + r * a.out_stride;
-        uint32_t cnt = 0;
+    // walker state; positions are relative to `org` (record start rounded down to a group)
+    bool active = false, done = false;
+    size_t org = 0, r_cur = 0;
+    int32_t end32 = 0, pos32 = 0, start32 = 0, hi32 = 0, lo32 = 0;
+    uint32_t mask = 0, base = 0, depth = 0, mlen = 0, mid = 0, cnt = 0;
+    int32_t *outp = nullptr;
 
-        size_t wb;       // window covers symbols [wb, wb + 16), wb % 8 == 0 (global sample index)
-        uint2 w0, w1;    // 8 symbols each
-        RawGroup<DT> nxt;  // group [wb + 16, wb + 24) in flight
-        auto prime = [&](size_t at) {
-            wb = at & ~(size_t)7;
-            RawGroup<DT> g0, g1;
-            load_group<DT>(g0, a.in, wb, n_total);
-            load_group<DT>(g1, a.in, wb + 8, n_total);
-            load_group<DT>(nxt, a.in, wb + 16, n_total);
-            w0 = quantize_group<DT, CELLS>(g0, qs, s_thr, qlo, qscale);
-            w1 = quantize_group<DT, CELLS>(g1, qs, s_thr, qlo, qscale);
-        };
-        prime(rs);
-
-        size_t pos = rs, start = rs;
-        uint32_t mask = root_mask, base = root_base, depth = 0, mlen = 0, mid = 0;
-        for (;;) {
-            if (pos >= wb + 16) {  // slide by one group; the next one is already in registers
-                w0 = w1;
-                w1 = quantize_group<DT, CELLS>(nxt, qs, s_thr, qlo, qscale);
-                wb += 8;
-                load_group<DT>(nxt, a.in, wb + 16, n_total);
-            }
-            const uint32_t off = (uint32_t)(pos - wb);
-            const uint32_t lo32 = (off & 8) ? w1.x : w0.x, hi32 = (off & 8) ? w1.y : w0.y;
-            const uint32_t byte = __byte_perm(lo32, hi32, off & 7) & 0xffu;
-            uint32_t c = byte;
-            if constexpr (DT == ECGB_U8) c = s_cls[byte];
-            const bool have = pos < re;
-            const bool ok = have && c < kNoClass && ((mask >> c) & 1u);
-            if (ok) {
-                const uint32_t idx = base + __popc(mask & ((1u << c) - 1u));
-                const uint2 nd = idx < S ? s_nodes[idx] : __ldg(a.nodes + idx);
-                mask = nd.x;
-                base = nd.y >> 16;
-                const uint32_t tok = nd.y & 0xFFFFu;
-                pos++;
-                depth++;
-                if (tok != kNoTok) { mlen = depth; mid = tok; }
-            } else if (depth == 0) {
-                if (!have) break;  // record exhausted at a token boundary
-                // a byte that occurs in no merge: its own single-byte token (lib.rs:155-157)
-                if (cnt < a.out_stride) outp[cnt] = (int32_t)byte;
-                cnt++;
-                pos++;
-                start = pos;
-            } else {  // walk ended: emit the longest terminal, resume right after it
-                if (cnt < a.out_stride) outp[cnt] = (int32_t)mid;
-                cnt++;
-                start += mlen;
-                if (start < wb) prime(start);
-                pos = start;
-                depth = 0;
-                mlen = 0;
-                mask = root_mask;
-                base = root_base;
+    for (;;) {
+        // ------------------------------------------------ record switch + refill (convergent)
+        if (!active && !done) {
+            if (r_next < r_hi) {
+                r_cur = r_next;
+                r_next += blockDim.x;
+                const size_t rs = a.offsets ? (size_t)a.offsets[r_cur] : r_cur * a.rec_len;
+                const size_t re = a.offsets ? (size_t)a.offsets[r_cur + 1] : rs + a.rec_len;
+                org = rs & ~(size_t)(kGroup - 1);
+                end32 = (int32_t)(re - org);
+                pos32 = start32 = (int32_t)(rs - org);
+                hi32 = lo32 = 0;
+                const uint2 root = s_nodes[0];
+                mask = root.x;
+                base = root.y >> 16;
+                depth = mlen = mid = cnt = 0;
+                outp = a.tokens + r_cur * a.out_stride;
+                active = true;
+            } else {
+                done = true;
             }
         }
-        a.lens[r] = (int32_t)cnt;
+        if (__all_sync(FULL, done)) break;
+#pragma unroll 1
+        for (int g = 0; g < kRing / kGroup; g++) {
+            // keep everything from the token start on, or the last 32 symbols of a long walk
+            const int32_t keep = max(start32, pos32 - 32) & ~(kGroup - 1);
+            const bool want = active && hi32 < end32 && hi32 + kGroup - keep <= kRing;
+            if (!__any_sync(FULL, want)) break;
+            if (want) {
+                const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, qs, s_thr, qlo, qscale);
+                *reinterpret_cast<uint4 *>(ring + (hi32 & (kRing - 1))) = sy;
+                hi32 += kGroup;
+                lo32 = max(lo32, hi32 - kRing);
+            }
+        }
+        // ------------------------------------------------ walk (convergent trie steps)
+        for (;;) {
+            const bool have = pos32 < end32;
+            const bool stall = active && have && pos32 >= hi32;
+            if (__any_sync(FULL, stall || (!active && !done))) break;
+            if (!active) continue;  // only lanes whose CTA range is exhausted
+            const uint32_t byte = ring[pos32 & (kRing - 1)];
+            uint32_t c = byte;
+            if constexpr (DT == ECGB_U8) c = s_cls[byte];
+            const bool okm = have && c < kNoClass && ((mask >> c) & 1u);
+            // a failed step re-reads the root, which is also the state a new token starts from
+            const uint32_t idx = okm ? base + __popc(mask & ((1u << c) - 1u)) : 0u;
+            const uint2 nd = idx < S ? s_nodes[idx] : __ldg(a.nodes + idx);
+            if (okm) {
+                const uint32_t tok = nd.y & 0xFFFFu;
+                pos32++;
+                depth++;
+                if (tok != kNoTok) { mlen = depth; mid = tok; }
+            } else if (depth != 0) {  // walk ended: emit the longest terminal, resume right after it
+                if (cnt < a.out_stride) outp[cnt] = (int32_t)mid;
+                cnt++;
+                start32 += (int32_t)mlen;
+                pos32 = start32;
+                depth = 0;
+                mlen = 0;
+                if (start32 < lo32) {  // reach-back beyond the ring (very long walk): refetch from there
+                    lo32 = hi32 = start32 & ~(kGroup - 1);
+                    org += (size_t)lo32;  // re-base so that ring offsets stay group aligned at zero
+                    end32 -= lo32;
+                    start32 -= lo32;
+                    pos32 = start32;
+                    lo32 = hi32 = 0;
+                }
+            } else if (!have) {  // record exhausted at a token boundary
+                a.lens[r_cur] = (int32_t)cnt;
+                active = false;
+            } else {  // a byte that occurs in no merge: its own single-byte token (lib.rs:155-157)
+                if (cnt < a.out_stride) outp[cnt] = (int32_t)byte;
+                cnt++;
+                pos32++;
+                start32 = pos32;
+            }
+            mask = nd.x;
+            base = nd.y >> 16;
+        }
     }
 }
 
@@ -243,16 +266,16 @@ static int launch_encode_t(const EncArgs &a, int exact_cells, int device, cudaSt
     ECGB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const size_t aux = DT == ECGB_U8 ? 256 : sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32;
     EncArgs args = a;
-    size_t budget = (size_t)smem_max > aux + 1024 ? (size_t)smem_max - aux - 1024 : 0;
-    args.smem_nodes = (uint32_t)std::min<size_t>(a.n_nodes, budget / 8);
-    if (args.smem_nodes < 1) return fail(ECGB_EUNSUPPORTED, "device shared memory too small for the trie root");
-    size_t smem = (((size_t)args.smem_nodes * 8 + 15) & ~(size_t)15) + aux;
-
     // one walker per record; CTAs get equal contiguous record ranges
     size_t grid = std::min<size_t>((size_t)sms, (a.n_rec + 31) / 32);
     if (grid < 1) grid = 1;
     size_t per_cta = (a.n_rec + grid - 1) / grid;
     int block = (int)std::min<size_t>(1024, ((per_cta + 31) / 32) * 32);
+    const size_t rings = (size_t)block * kRingStride;
+    size_t budget = (size_t)smem_max > aux + rings + 1024 ? (size_t)smem_max - aux - rings - 1024 : 0;
+    args.smem_nodes = (uint32_t)std::min<size_t>(a.n_nodes, budget / 8);
+    if (args.smem_nodes < 1) return fail(ECGB_EUNSUPPORTED, "device shared memory too small for the trie root");
+    size_t smem = (((size_t)args.smem_nodes * 8 + 15) & ~(size_t)15) + aux + rings;
     auto kern = exact_cells ? encode_kernel<DT, true> : encode_kernel<DT, false>;
     ECGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, block, smem, st>>>(args);
@@ -281,7 +304,8 @@ extern "C" int ecgb_encode_symbols(const ecgb_vocab *v, const uint8_t *d_sym, si
     if (n_rec == 0) return ECGB_OK;
     ECGB_REQUIRE(d_len && (d_tokens || out_stride == 0), "NULL output buffer");
     ECGB_REQUIRE(d_sym || (rec_len == 0 && !d_offsets), "d_sym is NULL");
-    ECGB_REQUIRE(((uintptr_t)d_sym & 7) == 0, "d_sym must be 8-byte aligned");
+    ECGB_REQUIRE(((uintptr_t)d_sym & 15) == 0, "d_sym must be 16-byte aligned");
+    ECGB_REQUIRE(rec_len < (1ull << 31), "records longer than 2^31 symbols are not supported");
     const VocabView *vv = ecgb_vocab_view(v);
     int device = ecgb_vocab_device(v);
     DeviceGuard g(device);
@@ -307,6 +331,7 @@ extern "C" int ecgb_encode_batch(const ecgb_vocab *v, const ecgb_quantizer *q, c
     if (n_rec == 0) return ECGB_OK;
     ECGB_REQUIRE(d_in && d_len && (d_tokens || out_stride == 0), "NULL buffer");
     ECGB_REQUIRE(((uintptr_t)d_in & 15) == 0, "d_in must be 16-byte aligned");
+    ECGB_REQUIRE(rec_len < (1ull << 31), "records longer than 2^31 samples are not supported");
     const VocabView *vv = ecgb_vocab_view(v);
     int device = ecgb_vocab_device(v);
     ECGB_REQUIRE(device == q->device, "vocab (device %d) and quantizer (device %d) live on different devices", device, q->device);
