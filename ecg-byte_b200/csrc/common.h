@@ -64,7 +64,7 @@ struct QuantTables {
 };
 
 struct VocabView {
-    const uint2 *d_nodes;   // compact nodes: x = child mask (bit c = class c), y = base << 16 | token
+    const uint2 *d_nodes;   // compact nodes: x = child mask (bit c = class c), y = base << 16 | (token + 1)
     uint32_t n_nodes;
     uint32_t smem_nodes;    // leading nodes staged in shared memory
     const uint8_t *d_cls;   // byte -> class (0..30) or 31 = no child anywhere

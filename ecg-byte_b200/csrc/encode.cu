@@ -41,7 +41,6 @@ struct EncArgs {
     QuantTables qt;
 };
 
-constexpr uint32_t kNoTok = 0xFFFFu;
 constexpr uint32_t kNoClass = 31u;
 
 // ---- 16-sample groups: the unit a walker loads, quantises and appends to its ring ----
@@ -55,9 +54,11 @@ constexpr int kRingStride = 80;   // bytes between rings: 16-byte stores of 8 la
 constexpr int kGroup = 16;
 
 // 16 samples at global index g (g % 16 == 0) -> 16 symbol classes, one per byte.
+// Positions at or beyond `valid` (record end) become the sentinel class 31, which has no
+// edge anywhere in the trie and therefore ends every walk.
 template <int DT, bool CELLS>
-__device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_total, const void *qsmem,
-                                         const void *thr_smem, float lo, float scale) {
+__device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_total, int valid, const void *qsmem,
+                                         const void *thr_smem, const uint8_t *s_cls, float lo, float scale) {
     using T = typename ElemOf<DT>::T;
     const T *p = static_cast<const T *>(base) + g;
     constexpr int NV = sizeof(T);  // 16-byte vectors per group
@@ -71,22 +72,45 @@ __device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_to
         for (int k = 0; k < kGroup; k++) tmp[k] = (g + k < n_total) ? p[k] : T(0);
         memcpy(raw, tmp, sizeof(raw));
     }
-    if constexpr (DT == ECGB_U8) {
-        return raw[0];  // text bytes; the class lookup happens per step
-    } else {
-        using Thr = typename SampleTraits<DT>::Thr;
-        const T *e = reinterpret_cast<const T *>(raw);
-        uint32_t w[4] = {0, 0, 0, 0};
+    const T *e = reinterpret_cast<const T *>(raw);
+    uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < kGroup; k++) {
+    for (int k = 0; k < kGroup; k++) {
+        uint32_t q;
+        if constexpr (DT == ECGB_U8) {
+            q = s_cls[e[k]];
+        } else {
+            using Thr = typename SampleTraits<DT>::Thr;
             float sf;
             Thr s = to_thr(e[k], &sf);
-            uint32_t q = CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
-                               : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
-            w[k >> 2] |= q << ((k & 3) * 8);
+            q = CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
+                      : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
         }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+        w[k >> 2] |= q << ((k & 3) * 8);
     }
+    if (valid < kGroup) {  // the record ends inside (or before) this group
+#pragma unroll
+        for (int k = 0; k < kGroup; k++)
+            if (k >= valid) w[k >> 2] |= kNoClass << ((k & 3) * 8);  // classes are < 32: OR gives 31
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // One walker (thread) per record.  A warp alternates between two CONVERGENT phases so
@@ -94,11 +118,13 @@ __device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_to
 //   refill: every lane with room appends up to four 16-sample groups to its private ring
 //           (128-bit loads -> threshold classification -> one STS.128 per group); lanes
 //           that finished a record pick up their next one here;
-//   walk:   pure trie steps (one LDS.U8 symbol + one LDS.64 node per step) until some
-//           lane runs out of symbols or finishes its record.
+//   walk:   K = min over lanes of the symbols left in their rings (one REDUX) trie steps
+//           with no votes and no bounds checks inside: one LDS.U8 symbol + one LDS.64 node
+//           per step, token emission predicated.  The end of a record is a sentinel
+//           symbol in the ring, so it needs no test on the hot path.
 // All lanes consume ~1 symbol per step, so their rings drain in lockstep and nearly all
 // lanes take part in every refill.
-template <int DT, bool CELLS>
+template <int DT, bool CELLS, bool ALL_SMEM>
 __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     using Thr = typename ThrOf<DT>::T;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -110,7 +136,8 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     Thr *s_thr = reinterpret_cast<Thr *>(s_aux + sizeof(QuantSmem<Thr>));
     uint8_t *s_cls = s_aux;
     constexpr size_t kAux = DT == ECGB_U8 ? 256 : sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32;
-    uint8_t *ring = s_aux + kAux + (size_t)threadIdx.x * kRingStride;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_aux + kAux + (size_t)threadIdx.x * kRingStride);
+    const uint32_t nodes_sa = (uint32_t)__cvta_generic_to_shared(s_nodes);
 
     for (uint32_t i = threadIdx.x; i < a.smem_nodes; i += blockDim.x) s_nodes[i] = a.nodes[i];
     if constexpr (DT == ECGB_U8) {
@@ -123,9 +150,11 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
 
     const float qlo = a.qt.lo, qscale = a.qt.scale;
     const uint32_t S = a.smem_nodes;
+    const uint32_t stride = (uint32_t)a.out_stride;
     // explicit offsets: the buffer ends where the last record ends
     const size_t n_total = a.offsets ? (size_t)a.offsets[a.n_rec] : a.n_total;
     constexpr unsigned FULL = 0xffffffffu;
+    const uint2 root = s_nodes[0];
 
     // contiguous, even split of the records over the CTAs
     const size_t r_lo = (size_t)(((unsigned __int128)a.n_rec * blockIdx.x) / gridDim.x);
@@ -135,9 +164,14 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     // walker state; positions are relative to `org` (record start rounded down to a group)
     bool active = false, done = false;
     size_t org = 0, r_cur = 0;
-    int32_t end32 = 0, pos32 = 0, start32 = 0, hi32 = 0, lo32 = 0;
-    uint32_t mask = 0, base = 0, depth = 0, mlen = 0, mid = 0, cnt = 0;
+    int32_t end32 = 0;    // record end
+    int32_t pos32 = 0;    // next symbol to read
+    int32_t start32 = 0;  // start of the token being matched
+    int32_t mpos = 0;     // end of the longest terminal seen since start32
+    int32_t hi32 = 0, lo32 = 0;  // ring holds [lo32, hi32)
+    uint32_t mask = root.x, base = root.y >> 16, mid = 0, cnt = 0;
     int32_t *outp = nullptr;
+    sts_u8(ring, kNoClass);  // idle lanes sit on a sentinel
 
     for (;;) {
         // ------------------------------------------------ record switch + refill (convergent)
@@ -149,76 +183,87 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
                 const size_t re = a.offsets ? (size_t)a.offsets[r_cur + 1] : rs + a.rec_len;
                 org = rs & ~(size_t)(kGroup - 1);
                 end32 = (int32_t)(re - org);
-                pos32 = start32 = (int32_t)(rs - org);
+                pos32 = start32 = mpos = (int32_t)(rs - org);
                 hi32 = lo32 = 0;
-                const uint2 root = s_nodes[0];
                 mask = root.x;
                 base = root.y >> 16;
-                depth = mlen = mid = cnt = 0;
+                mid = cnt = 0;
                 outp = a.tokens + r_cur * a.out_stride;
                 active = true;
             } else {
                 done = true;
+                pos32 = start32 = mpos = hi32 = lo32 = end32 = 0;
+                sts_u8(ring, kNoClass);
             }
         }
         if (__all_sync(FULL, done)) break;
 #pragma unroll 1
         for (int g = 0; g < kRing / kGroup; g++) {
-            // keep everything from the token start on, or the last 32 symbols of a long walk
+            // keep everything from the token start on, or the last 32 symbols of a long walk;
+            // the group that holds the end-of-record sentinel is part of the stream
             const int32_t keep = max(start32, pos32 - 32) & ~(kGroup - 1);
-            const bool want = active && hi32 < end32 && hi32 + kGroup - keep <= kRing;
+            const bool want = active && hi32 <= end32 && hi32 + kGroup - keep <= kRing;
             if (!__any_sync(FULL, want)) break;
             if (want) {
-                const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, qs, s_thr, qlo, qscale);
-                *reinterpret_cast<uint4 *>(ring + (hi32 & (kRing - 1))) = sy;
+                const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, qs, s_thr, s_cls,
+                                                    qlo, qscale);
+                sts_u128(ring + (uint32_t)(hi32 & (kRing - 1)), sy);
                 hi32 += kGroup;
                 lo32 = max(lo32, hi32 - kRing);
             }
         }
         // ------------------------------------------------ walk (convergent trie steps)
         for (;;) {
-            const bool have = pos32 < end32;
-            const bool stall = active && have && pos32 >= hi32;
-            if (__any_sync(FULL, stall || (!active && !done))) break;
-            if (!active) continue;  // only lanes whose CTA range is exhausted
-            const uint32_t byte = ring[pos32 & (kRing - 1)];
-            uint32_t c = byte;
-            if constexpr (DT == ECGB_U8) c = s_cls[byte];
-            const bool okm = have && c < kNoClass && ((mask >> c) & 1u);
-            // a failed step re-reads the root, which is also the state a new token starts from
-            const uint32_t idx = okm ? base + __popc(mask & ((1u << c) - 1u)) : 0u;
-            const uint2 nd = idx < S ? s_nodes[idx] : __ldg(a.nodes + idx);
-            if (okm) {
-                const uint32_t tok = nd.y & 0xFFFFu;
-                pos32++;
-                depth++;
-                if (tok != kNoTok) { mlen = depth; mid = tok; }
-            } else if (depth != 0) {  // walk ended: emit the longest terminal, resume right after it
-                if (cnt < a.out_stride) outp[cnt] = (int32_t)mid;
-                cnt++;
-                start32 += (int32_t)mlen;
-                pos32 = start32;
-                depth = 0;
-                mlen = 0;
-                if (start32 < lo32) {  // reach-back beyond the ring (very long walk): refetch from there
-                    lo32 = hi32 = start32 & ~(kGroup - 1);
-                    org += (size_t)lo32;  // re-base so that ring offsets stay group aligned at zero
-                    end32 -= lo32;
-                    start32 -= lo32;
-                    pos32 = start32;
-                    lo32 = hi32 = 0;
+            // idle lanes (done, or waiting for a record) never limit K; a lane that needs a
+            // record or symbols forces K = 0, i.e. the refill phase
+            const uint32_t avail = done ? 0x7fffffffu : (active ? (uint32_t)max(hi32 - pos32, 0) : 0u);
+            uint32_t K = __reduce_min_sync(FULL, avail);
+            if (K == 0) break;
+#pragma unroll 1
+            for (; K > 0; K--) {
+                const uint32_t c = lds_u8(ring + (uint32_t)(pos32 & (kRing - 1)));
+                const uint32_t bit = 1u << c;  // the sentinel (31) never has an edge
+                const bool okm = (mask & bit) != 0;
+                // a failed step re-reads the root, which is also the state a new token starts from
+                const uint32_t idx = okm ? base + __popc(mask & (bit - 1u)) : 0u;
+                uint2 nd;
+                if (ALL_SMEM || idx < S) nd = lds_u64(nodes_sa + idx * 8u);
+                else nd = __ldg(a.nodes + idx);
+                const bool pending = pos32 != start32;
+                const bool emit = !okm && pending;  // walk ended: emit the longest terminal
+                if (emit && cnt < stride) outp[cnt] = (int32_t)mid;
+                cnt += emit ? 1u : 0u;
+                const uint32_t tok1 = nd.y & 0xFFFFu;  // token id + 1, 0 = not a token
+                const int32_t adv = pos32 + 1;
+                if (okm && tok1 != 0u) { mpos = adv; mid = tok1 - 1u; }
+                pos32 = okm ? adv : (emit ? mpos : pos32);
+                start32 = emit ? mpos : start32;
+                mask = nd.x;
+                base = nd.y >> 16;
+                if (!okm && (!pending || start32 < lo32)) {  // rare: nothing pending, or reach-back beyond the ring
+                    if (emit) {
+                        // very long walk: the restart point left the ring; refetch from there
+                        const int32_t shift = start32 & ~(kGroup - 1);
+                        org += (size_t)shift;
+                        end32 -= shift;
+                        start32 -= shift;
+                        pos32 = mpos = start32;
+                        hi32 = lo32 = 0;
+                        sts_u8(ring + (uint32_t)(pos32 & (kRing - 1)), kNoClass);  // park until the refill
+                    } else if (active && pos32 < hi32) {
+                        if (pos32 >= end32) {  // record exhausted at a token boundary
+                            a.lens[r_cur] = (int32_t)cnt;
+                            active = false;
+                        } else {  // a byte that occurs in no merge: its own token (lib.rs:155-157)
+                            const uint32_t byte = static_cast<const uint8_t *>(a.in)[org + (size_t)pos32];
+                            if (cnt < stride) outp[cnt] = (int32_t)byte;
+                            cnt++;
+                            pos32++;
+                            start32 = mpos = pos32;
+                        }
+                    }
                 }
-            } else if (!have) {  // record exhausted at a token boundary
-                a.lens[r_cur] = (int32_t)cnt;
-                active = false;
-            } else {  // a byte that occurs in no merge: its own single-byte token (lib.rs:155-157)
-                if (cnt < a.out_stride) outp[cnt] = (int32_t)byte;
-                cnt++;
-                pos32++;
-                start32 = pos32;
             }
-            mask = nd.x;
-            base = nd.y >> 16;
         }
     }
 }
@@ -276,7 +321,9 @@ static int launch_encode_t(const EncArgs &a, int exact_cells, int device, cudaSt
     args.smem_nodes = (uint32_t)std::min<size_t>(a.n_nodes, budget / 8);
     if (args.smem_nodes < 1) return fail(ECGB_EUNSUPPORTED, "device shared memory too small for the trie root");
     size_t smem = (((size_t)args.smem_nodes * 8 + 15) & ~(size_t)15) + aux + rings;
-    auto kern = exact_cells ? encode_kernel<DT, true> : encode_kernel<DT, false>;
+    const bool all_smem = args.smem_nodes == a.n_nodes;
+    auto kern = exact_cells ? (all_smem ? encode_kernel<DT, true, true> : encode_kernel<DT, true, false>)
+                            : (all_smem ? encode_kernel<DT, false, true> : encode_kernel<DT, false, false>);
     ECGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, block, smem, st>>>(args);
     ECGB_CUDA(cudaGetLastError());

@@ -6,7 +6,7 @@
 // resident on the device:
 //   compact node (8 bytes, alphabets of <= 31 symbol classes -- every ECG-Byte
 //   vocabulary: 26 letters):  x = child bitmap over classes,
-//                             y = first_child << 16 | token_id (0xFFFF = not a token)
+//                             y = first_child << 16 | (token_id + 1)  (0 = not a token)
 //   child(c) = first_child + popc(bitmap & ((1 << c) - 1))          -- no hashing, one
 //   8-byte shared-memory load per trie step.
 //   wide node (40 bytes, any byte alphabet): 256-bit bitmap, first_child, token_id.
@@ -153,7 +153,7 @@ extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_of
             uint32_t mask = 0;
             for (auto &kv : nd.child)
                 if (cls[kv.first] < 31) mask |= 1u << cls[kv.first];
-            uint32_t tok = nd.token >= 0 ? (uint32_t)nd.token : 0xFFFFu;
+            uint32_t tok = nd.token >= 0 ? (uint32_t)nd.token + 1u : 0u;
             words[2 * i] = mask;
             words[2 * i + 1] = (first_child[i] << 16) | tok;
         }
