@@ -50,17 +50,17 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSymbols = 26;    // len(ALPHABET), tokenizer_utils.py:12
 constexpr int kNumThresholds = 25;
-constexpr int kCells = 1024;       // uniform pre-classification cells of the quantiser
+constexpr int kCells = 32;         // pre-classification cells of the quantiser (26 used)
 
 // Device-resident quantiser tables.  A sample s is mapped to a cell by monotone fp32
-// arithmetic  cell = clamp(int((float(s) - lo) * scale), 0, kCells-1); each cell holds at
-// most one threshold, so symbol = qbase[cell] + (s >= thr[cell]).
+// arithmetic  cell = min(uint((float(s) - lo) * scale), 25); the cells are half a bin out of
+// phase with the symbol bins, so cell k holds exactly threshold t_{k+1} and
+// symbol = cell + (s >= thr_cell[cell])  -- one 4-byte shared-memory load per sample.
 struct QuantTables {
     float lo, scale;
-    const void *d_cell_thr;     // ThrT[kCells]  (float for f32/i16, double for f64)
-    const uint8_t *d_cell_base; // u8[kCells]
+    const void *d_cell_thr;     // ThrT[kCells]  (float for f32/i16, double for f64); [25..] = NaN
     const void *d_thr;          // ThrT[kNumThresholds + 2] with sentinels (generic path)
-    int exact_cells;            // 1: the cell tables are usable; 0: fall back to d_thr search
+    int exact_cells;            // 1: the cell table is usable; 0: fall back to d_thr search
 };
 
 struct VocabView {

@@ -49,9 +49,8 @@ template <> struct ElemOf<ECGB_U8> { using T = uint8_t; };
 template <int DT> struct ThrOf { using T = typename SampleTraits<DT>::Thr; };
 template <> struct ThrOf<ECGB_U8> { using T = float; };
 
-constexpr int kRing = 64;         // symbols a walker keeps in shared memory
-constexpr int kRingStride = 80;   // bytes between rings: 16-byte stores of 8 lanes hit 8 distinct bank groups
 constexpr int kGroup = 16;
+constexpr int kMaxThreads = 768;  // walkers per CTA: 85 registers each, 24 warps per SM
 
 // 16 samples at global index g (g % 16 == 0) -> 16 symbol classes, one per byte.
 // Positions at or beyond `valid` (record end) become the sentinel class 31, which has no
@@ -106,26 +105,35 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_u128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// Symbol rings, one per walker, R symbols each, laid out TRANSPOSED inside a warp's
+// region: 4-byte word w of lane l lives at (w * 32 + l) * 4, so the bank of every access
+// is the lane id -- ring reads and writes are conflict-free wherever each lane's cursor is.
+template <int R>
+__device__ __forceinline__ uint32_t ring_addr(uint32_t lane_base, int32_t pos) {
+    const uint32_t o = (uint32_t)pos & (uint32_t)(R - 1);
+    return lane_base + ((o & ~3u) << 5) + (o & 3u);
+}
+
 // One walker (thread) per record.  A warp alternates between two CONVERGENT phases so
 // that the 32 walkers never serialise on each other's bookkeeping:
-//   refill: every lane with room appends up to four 16-sample groups to its private ring
-//           (128-bit loads -> threshold classification -> one STS.128 per group); lanes
-//           that finished a record pick up their next one here;
+//   refill: every lane with room appends 16-sample groups to its private ring (128-bit
+//           loads -> threshold classification -> four conflict-free STS.32 per group);
+//           lanes that finished a record pick up their next one here;
 //   walk:   K = min over lanes of the symbols left in their rings (one REDUX) trie steps
 //           with no votes and no bounds checks inside: one LDS.U8 symbol + one LDS.64 node
 //           per step, token emission predicated.  The end of a record is a sentinel
 //           symbol in the ring, so it needs no test on the hot path.
 // All lanes consume ~1 symbol per step, so their rings drain in lockstep and nearly all
 // lanes take part in every refill.
-template <int DT, bool CELLS, bool ALL_SMEM>
-__global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
+template <int DT, bool CELLS, bool ALL_SMEM, int R>
+__global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
     using Thr = typename ThrOf<DT>::T;
     extern __shared__ __align__(16) uint8_t smem[];
     uint2 *s_nodes = reinterpret_cast<uint2 *>(smem);
@@ -136,7 +144,8 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
     Thr *s_thr = reinterpret_cast<Thr *>(s_aux + sizeof(QuantSmem<Thr>));
     uint8_t *s_cls = s_aux;
     constexpr size_t kAux = DT == ECGB_U8 ? 256 : sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_aux + kAux + (size_t)threadIdx.x * kRingStride);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_aux + kAux) + (threadIdx.x >> 5) * (32u * R) +
+                          (threadIdx.x & 31u) * 4u;
     const uint32_t nodes_sa = (uint32_t)__cvta_generic_to_shared(s_nodes);
 
     for (uint32_t i = threadIdx.x; i < a.smem_nodes; i += blockDim.x) s_nodes[i] = a.nodes[i];
@@ -198,30 +207,34 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
         }
         if (__all_sync(FULL, done)) break;
 #pragma unroll 1
-        for (int g = 0; g < kRing / kGroup; g++) {
+        for (int g = 0; g < R / kGroup; g++) {
             // keep everything from the token start on, or the last 32 symbols of a long walk;
             // the group that holds the end-of-record sentinel is part of the stream
             const int32_t keep = max(start32, pos32 - 32) & ~(kGroup - 1);
-            const bool want = active && hi32 <= end32 && hi32 + kGroup - keep <= kRing;
+            const bool want = active && hi32 <= end32 && hi32 + kGroup - keep <= R;
             if (!__any_sync(FULL, want)) break;
             if (want) {
                 const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, qs, s_thr, s_cls,
                                                     qlo, qscale);
-                sts_u128(ring + (uint32_t)(hi32 & (kRing - 1)), sy);
+                const uint32_t wa = ring_addr<R>(ring, hi32);
+                sts_u32(wa, sy.x);
+                sts_u32(wa + 128u, sy.y);
+                sts_u32(wa + 256u, sy.z);
+                sts_u32(wa + 384u, sy.w);
                 hi32 += kGroup;
-                lo32 = max(lo32, hi32 - kRing);
+                lo32 = max(lo32, hi32 - R);
             }
         }
         // ------------------------------------------------ walk (convergent trie steps)
         for (;;) {
-            // idle lanes (done, or waiting for a record) never limit K; a lane that needs a
-            // record or symbols forces K = 0, i.e. the refill phase
+            // idle lanes (done) never limit K; a lane that needs a record or symbols forces
+            // K = 0, i.e. the refill phase
             const uint32_t avail = done ? 0x7fffffffu : (active ? (uint32_t)max(hi32 - pos32, 0) : 0u);
             uint32_t K = __reduce_min_sync(FULL, avail);
             if (K == 0) break;
 #pragma unroll 1
             for (; K > 0; K--) {
-                const uint32_t c = lds_u8(ring + (uint32_t)(pos32 & (kRing - 1)));
+                const uint32_t c = lds_u8(ring_addr<R>(ring, pos32));
                 const uint32_t bit = 1u << c;  // the sentinel (31) never has an edge
                 const bool okm = (mask & bit) != 0;
                 // a failed step re-reads the root, which is also the state a new token starts from
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(1024, 1) encode_kernel(EncArgs a) {
                         start32 -= shift;
                         pos32 = mpos = start32;
                         hi32 = lo32 = 0;
-                        sts_u8(ring + (uint32_t)(pos32 & (kRing - 1)), kNoClass);  // park until the refill
+                        sts_u8(ring_addr<R>(ring, pos32), kNoClass);  // park until the refill
                     } else if (active && pos32 < hi32) {
                         if (pos32 >= end32) {  // record exhausted at a token boundary
                             a.lens[r_cur] = (int32_t)cnt;
@@ -303,6 +316,12 @@ __global__ void __launch_bounds__(256) encode_wide_kernel(const uint8_t *__restr
     }
 }
 
+template <int DT, int R>
+static auto pick_kernel(bool cells, bool all_smem) {
+    return cells ? (all_smem ? encode_kernel<DT, true, true, R> : encode_kernel<DT, true, false, R>)
+                 : (all_smem ? encode_kernel<DT, false, true, R> : encode_kernel<DT, false, false, R>);
+}
+
 template <int DT>
 static int launch_encode_t(const EncArgs &a, int exact_cells, int device, cudaStream_t st) {
     using Thr = typename ThrOf<DT>::T;
@@ -315,15 +334,18 @@ static int launch_encode_t(const EncArgs &a, int exact_cells, int device, cudaSt
     size_t grid = std::min<size_t>((size_t)sms, (a.n_rec + 31) / 32);
     if (grid < 1) grid = 1;
     size_t per_cta = (a.n_rec + grid - 1) / grid;
-    int block = (int)std::min<size_t>(1024, ((per_cta + 31) / 32) * 32);
-    const size_t rings = (size_t)block * kRingStride;
+    int block = (int)std::min<size_t>(kMaxThreads, ((per_cta + 31) / 32) * 32);
+    // 128-symbol rings when the whole trie still fits beside them, else 64-symbol rings
+    const size_t nodes_all = (((size_t)a.n_nodes * 8 + 15) & ~(size_t)15);
+    int ring = 128;
+    if (nodes_all + aux + (size_t)block * 128 + 1024 > (size_t)smem_max) ring = 64;
+    const size_t rings = (size_t)block * ring;
     size_t budget = (size_t)smem_max > aux + rings + 1024 ? (size_t)smem_max - aux - rings - 1024 : 0;
     args.smem_nodes = (uint32_t)std::min<size_t>(a.n_nodes, budget / 8);
     if (args.smem_nodes < 1) return fail(ECGB_EUNSUPPORTED, "device shared memory too small for the trie root");
     size_t smem = (((size_t)args.smem_nodes * 8 + 15) & ~(size_t)15) + aux + rings;
     const bool all_smem = args.smem_nodes == a.n_nodes;
-    auto kern = exact_cells ? (all_smem ? encode_kernel<DT, true, true> : encode_kernel<DT, true, false>)
-                            : (all_smem ? encode_kernel<DT, false, true> : encode_kernel<DT, false, false>);
+    auto kern = ring == 128 ? pick_kernel<DT, 128>(exact_cells != 0, all_smem) : pick_kernel<DT, 64>(exact_cells != 0, all_smem);
     ECGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, block, smem, st>>>(args);
     ECGB_CUDA(cudaGetLastError());

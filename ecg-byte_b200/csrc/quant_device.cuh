@@ -11,37 +11,30 @@ template <> struct SampleTraits<ECGB_F32> { using In = float;   using Thr = floa
 template <> struct SampleTraits<ECGB_F64> { using In = double;  using Thr = double; static constexpr int kPer16B = 2; };
 template <> struct SampleTraits<ECGB_I16> { using In = int16_t; using Thr = float;  static constexpr int kPer16B = 8; };
 
-// Shared-memory image of the quantiser tables: one entry per cell, read with one LDS.
-template <typename Thr> struct Cell;
-template <> struct __align__(8) Cell<float> { float thr; uint32_t base; };
-template <> struct __align__(16) Cell<double> { double thr; uint32_t base; uint32_t pad; };
-
+// Shared-memory image of the quantiser cell table.
 template <typename Thr>
 struct QuantSmem {
-    Cell<Thr> cell[kCells];
+    Thr cell_thr[kCells];
 };
 
 template <typename Thr>
 __device__ __forceinline__ void load_quant_smem(QuantSmem<Thr> *s, const QuantTables &t) {
     const Thr *g_thr = static_cast<const Thr *>(t.d_cell_thr);
-    for (int i = threadIdx.x; i < kCells; i += blockDim.x) {
-        s->cell[i].thr = g_thr[i];
-        s->cell[i].base = t.d_cell_base[i];
-    }
+    for (int i = threadIdx.x; i < kCells; i += blockDim.x) s->cell_thr[i] = g_thr[i];
 }
 
 // cell index: monotone non-decreasing in the sample (every step is a monotone rounding
 // operation); NaN and negative offsets saturate to cell 0, large ones to the last cell.
 __device__ __forceinline__ uint32_t cell_of(float sf, float lo, float scale) {
     const float x = __fmul_rn(__fsub_rn(sf, lo), scale);
-    return min(__float2uint_rz(x), (uint32_t)(kCells - 1));
+    return min(__float2uint_rz(x), (uint32_t)kNumThresholds);
 }
 
 template <typename Thr>
 __device__ __forceinline__ uint32_t classify(Thr s, float sf, float lo, float scale,
                                              const QuantSmem<Thr> *q) {
-    const Cell<Thr> c = q->cell[cell_of(sf, lo, scale)];
-    return c.base + (s >= c.thr ? 1u : 0u);
+    const uint32_t c = cell_of(sf, lo, scale);
+    return c + (s >= q->cell_thr[c] ? 1u : 0u);
 }
 
 // generic (always valid) path: count thresholds <= s.  thr has kNumThresholds entries.

@@ -90,7 +90,7 @@ static int host_cell(float sf, float lo, float scale) {
     volatile float x = d * scale;
     float y = x;
     if (!(y >= 0.0f)) y = 0.0f;  // also NaN -> 0 (fmaxf(NaN, 0) == 0)
-    if (y > (float)(kCells - 1)) y = (float)(kCells - 1);
+    if (y > (float)kNumThresholds) y = (float)kNumThresholds;
     return (int)y;
 }
 
@@ -218,49 +218,31 @@ extern "C" int ecgb_quantizer_create(double p1, double p99, ecgb_dtype dtype, do
         q->thr[k - 1] = t;
     }
 
-    // ---- cell tables ----
+    // ---- cell table: cell k must hold exactly threshold t_{k+1} ----
     const bool f64 = dtype == ECGB_F64;
     const size_t thr_sz = f64 ? 8 : 4;
     float lo_f = 0.f, scale_f = 0.f;
     int exact = 0;
-    int cell_of_thr[kNumThresholds];
     double t1 = q->thr[0], t25 = q->thr[kNumThresholds - 1];
     if (std::isfinite(t1) && std::isfinite(t25) && t25 > t1) {
-        float t1f = (float)t1, t25f = (float)t25;
-        float span = t25f - t1f;
-        if (std::isfinite(span) && span > 0.f) {
-            scale_f = (float)(kCells - 4) / span;
-            lo_f = t1f - 2.0f / scale_f;
-            if (std::isfinite(scale_f) && std::isfinite(lo_f) && scale_f > 0.f) {
-                exact = 1;
-                bool used[kCells] = {false};
-                for (int k = 0; k < kNumThresholds; k++) {
-                    int c = host_cell((float)q->thr[k], lo_f, scale_f);
-                    cell_of_thr[k] = c;
-                    if (used[c]) exact = 0;  // two thresholds in one cell: use the search path
-                    used[c] = true;
-                }
-            }
+        const double bin = (t25 - t1) / (double)(kNumThresholds - 1);
+        scale_f = (float)(1.0 / bin);
+        lo_f = (float)(t1 - 0.5 * bin);
+        if (std::isfinite(scale_f) && std::isfinite(lo_f) && scale_f > 0.f) {
+            exact = 1;
+            for (int k = 0; k < kNumThresholds; k++)
+                if (!std::isfinite(q->thr[k]) || host_cell((float)q->thr[k], lo_f, scale_f) != k) exact = 0;
         }
     }
-    size_t bytes = thr_sz * kCells + kCells + thr_sz * (kNumThresholds + 2) + 64;
+    size_t bytes = thr_sz * kCells + thr_sz * (kNumThresholds + 2) + 64;
     std::vector<uint8_t> host(bytes, 0);
     uint8_t *h_cell_thr = host.data();
     uint8_t *h_thr = host.data() + thr_sz * kCells;
-    uint8_t *h_base = h_thr + thr_sz * (kNumThresholds + 2);
     const double nan = std::numeric_limits<double>::quiet_NaN();
     auto put = [&](uint8_t *base, int i, double v) {
         if (f64) { std::memcpy(base + 8 * i, &v, 8); } else { float f = (float)v; std::memcpy(base + 4 * i, &f, 4); }
     };
-    for (int c = 0; c < kCells; c++) put(h_cell_thr, c, nan);
-    if (exact) {
-        for (int c = 0; c < kCells; c++) {
-            int below = 0;
-            for (int k = 0; k < kNumThresholds; k++) below += cell_of_thr[k] < c;
-            h_base[c] = (uint8_t)below;
-        }
-        for (int k = 0; k < kNumThresholds; k++) put(h_cell_thr, cell_of_thr[k], q->thr[k]);
-    }
+    for (int c = 0; c < kCells; c++) put(h_cell_thr, c, c < kNumThresholds ? q->thr[c] : nan);
     for (int k = 0; k < kNumThresholds; k++) put(h_thr, k, q->thr[k]);
     put(h_thr, kNumThresholds, nan);
     put(h_thr, kNumThresholds + 1, nan);
@@ -274,7 +256,6 @@ extern "C" int ecgb_quantizer_create(double p1, double p99, ecgb_dtype dtype, do
     q->tab.lo = lo_f; q->tab.scale = scale_f; q->tab.exact_cells = exact;
     q->tab.d_cell_thr = d;
     q->tab.d_thr = d + thr_sz * kCells;
-    q->tab.d_cell_base = d + thr_sz * kCells + thr_sz * (kNumThresholds + 2);
     *out = q;
     return ECGB_OK;
 }
