@@ -121,15 +121,34 @@ __device__ __forceinline__ uint32_t ring_addr(uint32_t lane_base, int32_t pos) {
     return lane_base + ((o & ~3u) << 5) + (o & 3u);
 }
 
+// class of the single symbol at global index g (slow paths only)
+template <int DT, bool CELLS>
+__device__ __forceinline__ uint32_t class_at(const void *base, size_t g, const void *qsmem, const void *thr_smem,
+                                             const uint8_t *s_cls, float lo, float scale) {
+    using T = typename ElemOf<DT>::T;
+    const T v = static_cast<const T *>(base)[g];
+    if constexpr (DT == ECGB_U8) {
+        return s_cls[v];
+    } else {
+        using Thr = typename SampleTraits<DT>::Thr;
+        float sf;
+        Thr s = to_thr(v, &sf);
+        return CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
+                     : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
+    }
+}
+
 // One walker (thread) per record.  A warp alternates between two CONVERGENT phases so
 // that the 32 walkers never serialise on each other's bookkeeping:
 //   refill: every lane with room appends 16-sample groups to its private ring (128-bit
 //           loads -> threshold classification -> four conflict-free STS.32 per group);
-//           lanes that finished a record pick up their next one here;
+//           record ends, record switches and the (rare) walks longer than a ring are
+//           handled here, outside the hot loop;
 //   walk:   K = min over lanes of the symbols left in their rings (one REDUX) trie steps
-//           with no votes and no bounds checks inside: one LDS.U8 symbol + one LDS.64 node
-//           per step, token emission predicated.  The end of a record is a sentinel
-//           symbol in the ring, so it needs no test on the hot path.
+//           with no votes, no bounds checks and no branches inside: one LDS.U8 symbol +
+//           one LDS.64 node per step, token emission predicated.  The end of a record is
+//           a sentinel symbol in the ring (class 31 has no edge anywhere), on which a
+//           finished walker simply idles until the phase ends.
 // All lanes consume ~1 symbol per step, so their rings drain in lockstep and nearly all
 // lanes take part in every refill.
 template <int DT, bool CELLS, bool ALL_SMEM, int R>
@@ -164,6 +183,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
     const size_t n_total = a.offsets ? (size_t)a.offsets[a.n_rec] : a.n_total;
     constexpr unsigned FULL = 0xffffffffu;
     const uint2 root = s_nodes[0];
+    // breadth-first numbering: only the root has its first child at index 1, so
+    // "a walk is in progress" == (base != root_base)
+    const uint32_t root_base = root.y >> 16;
+
+    auto node_at = [&](uint32_t idx) -> uint2 {
+        if (ALL_SMEM || idx < S) return lds_u64(nodes_sa + idx * 8u);
+        return __ldg(a.nodes + idx);
+    };
 
     // contiguous, even split of the records over the CTAs
     const size_t r_lo = (size_t)(((unsigned __int128)a.n_rec * blockIdx.x) / gridDim.x);
@@ -173,17 +200,31 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
     // walker state; positions are relative to `org` (record start rounded down to a group)
     bool active = false, done = false;
     size_t org = 0, r_cur = 0;
-    int32_t end32 = 0;    // record end
-    int32_t pos32 = 0;    // next symbol to read
-    int32_t start32 = 0;  // start of the token being matched
-    int32_t mpos = 0;     // end of the longest terminal seen since start32
-    int32_t hi32 = 0, lo32 = 0;  // ring holds [lo32, hi32)
-    uint32_t mask = root.x, base = root.y >> 16, mid = 0, cnt = 0;
+    int32_t end32 = 0;  // record end
+    int32_t pos32 = 0;  // next symbol to read
+    int32_t mpos = 0;   // end of the longest terminal of the walk in progress (== pos32 at the root)
+    int32_t hi32 = 0;   // ring holds [max(hi32 - R, 0), hi32) and never drops symbols >= mpos
+    uint32_t mask = root.x, base = root_base, mid = 0, cnt = 0;
     int32_t *outp = nullptr;
     sts_u8(ring, kNoClass);  // idle lanes sit on a sentinel
 
     for (;;) {
-        // ------------------------------------------------ record switch + refill (convergent)
+        // ------------------------------------------------ phase boundary (convergent)
+        // (1) walkers parked on a class-31 symbol at the root: end of record, or a byte that
+        //     occurs in no merge and is its own token (text only; lib.rs:155-157)
+        while (active && base == root_base && pos32 < hi32 && lds_u8(ring_addr<R>(ring, pos32)) == kNoClass) {
+            if (pos32 >= end32) {
+                a.lens[r_cur] = (int32_t)cnt;
+                active = false;
+            } else {
+                const uint32_t byte = static_cast<const uint8_t *>(a.in)[org + (size_t)pos32];
+                if (cnt < stride) outp[cnt] = (int32_t)byte;
+                cnt++;
+                pos32++;
+                mpos = pos32;
+            }
+        }
+        // (2) next record
         if (!active && !done) {
             if (r_next < r_hi) {
                 r_cur = r_next;
@@ -192,90 +233,99 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
                 const size_t re = a.offsets ? (size_t)a.offsets[r_cur + 1] : rs + a.rec_len;
                 org = rs & ~(size_t)(kGroup - 1);
                 end32 = (int32_t)(re - org);
-                pos32 = start32 = mpos = (int32_t)(rs - org);
-                hi32 = lo32 = 0;
+                pos32 = mpos = (int32_t)(rs - org);
+                hi32 = 0;
                 mask = root.x;
-                base = root.y >> 16;
+                base = root_base;
                 mid = cnt = 0;
                 outp = a.tokens + r_cur * a.out_stride;
                 active = true;
             } else {
                 done = true;
-                pos32 = start32 = mpos = hi32 = lo32 = end32 = 0;
+                pos32 = mpos = hi32 = end32 = 0;
+                mask = root.x;
+                base = root_base;
                 sts_u8(ring, kNoClass);
             }
         }
         if (__all_sync(FULL, done)) break;
+        // (3) refill: append groups while the ring keeps everything from mpos on; the group that
+        //     holds the end-of-record sentinel is part of the stream
+        bool again;
+        do {
 #pragma unroll 1
-        for (int g = 0; g < R / kGroup; g++) {
-            // keep everything from the token start on, or the last 32 symbols of a long walk;
-            // the group that holds the end-of-record sentinel is part of the stream
-            const int32_t keep = max(start32, pos32 - 32) & ~(kGroup - 1);
-            const bool want = active && hi32 <= end32 && hi32 + kGroup - keep <= R;
-            if (!__any_sync(FULL, want)) break;
-            if (want) {
-                const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, qs, s_thr, s_cls,
-                                                    qlo, qscale);
-                const uint32_t wa = ring_addr<R>(ring, hi32);
-                sts_u32(wa, sy.x);
-                sts_u32(wa + 128u, sy.y);
-                sts_u32(wa + 256u, sy.z);
-                sts_u32(wa + 384u, sy.w);
-                hi32 += kGroup;
-                lo32 = max(lo32, hi32 - R);
+            for (int g = 0; g < R / kGroup; g++) {
+                const bool want = active && hi32 <= end32 && hi32 + kGroup - (mpos & ~(kGroup - 1)) <= R;
+                if (!__any_sync(FULL, want)) break;
+                if (want) {
+                    const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, qs, s_thr,
+                                                        s_cls, qlo, qscale);
+                    const uint32_t wa = ring_addr<R>(ring, hi32);
+                    sts_u32(wa, sy.x);
+                    sts_u32(wa + 128u, sy.y);
+                    sts_u32(wa + 256u, sy.z);
+                    sts_u32(wa + 384u, sy.w);
+                    hi32 += kGroup;
+                }
             }
-        }
+            // (4) a walk longer than the ring (no terminal for ~R symbols): finish that one walk
+            //     symbol by symbol from global memory, emit, and restart with an empty ring
+            const bool stuck = active && pos32 >= hi32 && hi32 <= end32;
+            if (stuck) {
+                for (;;) {
+                    const uint32_t c = pos32 < end32
+                                           ? class_at<DT, CELLS>(a.in, org + (size_t)pos32, qs, s_thr, s_cls, qlo, qscale)
+                                           : kNoClass;
+                    const uint32_t bit = 1u << c;
+                    if (!(mask & bit)) break;
+                    const uint2 nd = node_at(base + __popc(mask & (bit - 1u)));
+                    pos32++;
+                    if (nd.y & 0xFFFFu) { mpos = pos32; mid = (nd.y & 0xFFFFu) - 1u; }
+                    mask = nd.x;
+                    base = nd.y >> 16;
+                }
+                if (cnt < stride) outp[cnt] = (int32_t)mid;
+                cnt++;
+                const int32_t shift = mpos & ~(kGroup - 1);
+                org += (size_t)shift;
+                end32 -= shift;
+                mpos -= shift;
+                pos32 = mpos;
+                hi32 = 0;
+                mask = root.x;
+                base = root_base;
+            }
+            again = __any_sync(FULL, stuck);
+        } while (again);
+
         // ------------------------------------------------ walk (convergent trie steps)
-        for (;;) {
-            // idle lanes (done) never limit K; a lane that needs a record or symbols forces
-            // K = 0, i.e. the refill phase
-            const uint32_t avail = done ? 0x7fffffffu : (active ? (uint32_t)max(hi32 - pos32, 0) : 0u);
+        {
+            // idle lanes (done) never limit K; a lane that sits on its end-of-record sentinel
+            // ends the phase at once.  After the K steps control returns to the phase boundary,
+            // which also serves walkers parked on a byte that is its own token.
+            uint32_t avail = 0x7fffffffu;
+            if (!done) {
+                avail = active ? (uint32_t)max(hi32 - pos32, 0) : 0u;
+                if (active && base == root_base && pos32 >= end32) avail = 0u;
+            }
             uint32_t K = __reduce_min_sync(FULL, avail);
-            if (K == 0) break;
-#pragma unroll 1
+#pragma unroll 2
             for (; K > 0; K--) {
                 const uint32_t c = lds_u8(ring_addr<R>(ring, pos32));
                 const uint32_t bit = 1u << c;  // the sentinel (31) never has an edge
                 const bool okm = (mask & bit) != 0;
                 // a failed step re-reads the root, which is also the state a new token starts from
                 const uint32_t idx = okm ? base + __popc(mask & (bit - 1u)) : 0u;
-                uint2 nd;
-                if (ALL_SMEM || idx < S) nd = lds_u64(nodes_sa + idx * 8u);
-                else nd = __ldg(a.nodes + idx);
-                const bool pending = pos32 != start32;
-                const bool emit = !okm && pending;  // walk ended: emit the longest terminal
+                const uint2 nd = node_at(idx);
+                const bool emit = !okm && base != root_base;  // walk ended: emit the longest terminal
                 if (emit && cnt < stride) outp[cnt] = (int32_t)mid;
                 cnt += emit ? 1u : 0u;
                 const uint32_t tok1 = nd.y & 0xFFFFu;  // token id + 1, 0 = not a token
                 const int32_t adv = pos32 + 1;
                 if (okm && tok1 != 0u) { mpos = adv; mid = tok1 - 1u; }
-                pos32 = okm ? adv : (emit ? mpos : pos32);
-                start32 = emit ? mpos : start32;
+                pos32 = okm ? adv : mpos;  // at the root mpos == pos32: a parked walker stays put
                 mask = nd.x;
                 base = nd.y >> 16;
-                if (!okm && (!pending || start32 < lo32)) {  // rare: nothing pending, or reach-back beyond the ring
-                    if (emit) {
-                        // very long walk: the restart point left the ring; refetch from there
-                        const int32_t shift = start32 & ~(kGroup - 1);
-                        org += (size_t)shift;
-                        end32 -= shift;
-                        start32 -= shift;
-                        pos32 = mpos = start32;
-                        hi32 = lo32 = 0;
-                        sts_u8(ring_addr<R>(ring, pos32), kNoClass);  // park until the refill
-                    } else if (active && pos32 < hi32) {
-                        if (pos32 >= end32) {  // record exhausted at a token boundary
-                            a.lens[r_cur] = (int32_t)cnt;
-                            active = false;
-                        } else {  // a byte that occurs in no merge: its own token (lib.rs:155-157)
-                            const uint32_t byte = static_cast<const uint8_t *>(a.in)[org + (size_t)pos32];
-                            if (cnt < stride) outp[cnt] = (int32_t)byte;
-                            cnt++;
-                            pos32++;
-                            start32 = mpos = pos32;
-                        }
-                    }
-                }
             }
         }
     }
