@@ -296,6 +296,11 @@ def run_ours(args, rank, world, local_rank):
                          "(trie rebuilt per record as lib.rs:153-161 does); trie built once: %.0f records/s"
                          % (n_cpu, dt, rate_am)}
 
+    # ---- secondary metric: BPE-train merges/s (BASELINE.json config 1 scale), single GPU ----
+    train = None
+    if world == 1 and not args.no_train:
+        train = bench_train(dev, pct, peak)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -312,10 +317,42 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": traffic, "kernel": "ecgb::encode_kernel<F32>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "cpu_baseline": cpu,
+        "train": train,
         "clocks": clocks,
         "parity": {"records_checked": int(len(idx)), "ok": True},
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_train(dev, pct, peak):
+    """byte_pair_encoding on the config-1 corpus shape: 1,000 records = 6e7 symbols,
+    5,000 merges, whole loop on the device; checked against the oracle's merge list."""
+    import torch
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Trainer
+    f = np.load(FIXTURE)
+    x = torch.from_numpy(synth.corpus(0, 1000, L_SAMPLES, np.float32)).to(dev)
+    q = Quantizer(pct, dtype=torch.float32, device=dev)
+    sym = q.quantize(x).reshape(-1)
+    m = 5000
+    tr = Trainer(sym.numel(), m, device=dev)
+    best = None
+    for _ in range(3):
+        tr.load(sym)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        pairs, counts, ntied = tr.run(m)  # synchronises at the end
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    ok = bool(np.array_equal(pairs, f["pairs"].astype(np.uint32)) and np.array_equal(counts, f["counts"]))
+    if not ok:
+        raise SystemExit("bench.py: PARITY FAILURE (merge list differs from the oracle fixture)")
+    n = tr.lengths(m).astype(np.float64)
+    alg = float(np.sum(2.0 * (n[:-1] + n[1:])))  # SURVEY.md 8d: 2*(n_t + n_{t+1}) bytes per step
+    return {"metric": "BPE-train merges/sec", "value": m / best, "unit": "merges/s", "seconds": best,
+            "corpus_symbols": int(n[0]), "merges": m, "final_tokens": int(n[-1]),
+            "algorithmic_bytes": alg, "achieved_gbs": alg / best / 1e9, "frac_of_hbm_peak": alg / best / 1e9 / peak,
+            "gpu_launches": 2 * m + 1, "parity": "merge list == oracle fixture (5000 merges)"}
 
 
 def main():
@@ -330,6 +367,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=2048)
     ap.add_argument("--check", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

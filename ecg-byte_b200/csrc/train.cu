@@ -87,6 +87,7 @@ struct TrainView {
     uint32_t *tickets;        // [max_merges + 1] tile tickets, zero-initialised
     unsigned long long *tile_status;  // [max tiles]
     Boundary *boundary;       // this rank's boundary info (device)
+    unsigned long long *n_hist;  // [max_merges + 2] stream length before each step
     int rank, world;
 };
 
@@ -528,7 +529,10 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
             __threadfence();
             atomicExch(&v.tile_status[tile], pack_status(2, step, excl + (unsigned long long)tile_total));
             s_prefix = excl;
-            if (tile == ntiles - 1) v.dev->n[(step + 1) & 1] = excl + (unsigned long long)tile_total;
+            if (tile == ntiles - 1) {
+                v.dev->n[(step + 1) & 1] = excl + (unsigned long long)tile_total;
+                v.n_hist[step + 1] = excl + (unsigned long long)tile_total;
+            }
         }
         __syncthreads();
         const unsigned long long gofs = s_prefix;
@@ -648,6 +652,7 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tickets, 4 * ((size_t)max_merges + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tile_status, 8 * ntiles, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.n_hist, 8 * ((size_t)max_merges + 2), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->d_list, (size_t)(4 + 3 * (size_t)t->list_cap) * 4, true);
     if (rc) { ecgb_trainer_destroy(t); return rc; }
     t->v.rank = 0;
@@ -680,6 +685,8 @@ static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
     ECGB_CUDA(cudaMemsetAsync(t->v.delta.cnt, 0, dcap * 8, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.delta.used, 0, 8, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.tickets, 0, 4 * ((size_t)t->max_merges + 1), st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.n_hist, 0, 8 * ((size_t)t->max_merges + 2), st));
+    ECGB_CUDA(cudaMemcpyAsync(t->v.n_hist, &t->v.dev->n[0], 8, cudaMemcpyDeviceToDevice, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.best, 0, sizeof(Best) * ((size_t)t->max_merges + 1), st));
     ECGB_CUDA(cudaMemsetAsync(t->v.tile_status, 0, 8 * ((size_t)(t->capacity / kTile) + 2), st));
     t->steps_done = 0;
@@ -801,6 +808,18 @@ extern "C" int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t 
         ECGB_CUDA(cudaGetLastError());
         ECGB_CUDA(cudaMemcpy(h_ids + o, d_tmp, c * 4, cudaMemcpyDeviceToHost));
     }
+    return ECGB_OK;
+}
+
+// Length of this shard's token stream before merge step i, i in [0, n_steps]
+// (h_n[0] = corpus bytes, h_n[i] = tokens left after i merges): the n_t of the
+// algorithmic-bytes formula 2*(n_t + n_{t+1}) per step.
+extern "C" int ecgb_trainer_lengths(ecgb_trainer *t, uint32_t n_steps, uint64_t *h_n) {
+    ECGB_REQUIRE(t && h_n, "NULL argument");
+    ECGB_REQUIRE(n_steps <= t->max_merges, "n_steps out of range");
+    DeviceGuard g(t->device);
+    ECGB_CUDA(cudaDeviceSynchronize());
+    ECGB_CUDA(cudaMemcpy(h_n, t->v.n_hist, 8 * ((size_t)n_steps + 1), cudaMemcpyDeviceToHost));
     return ECGB_OK;
 }
 

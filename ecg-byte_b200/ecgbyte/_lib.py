@@ -55,6 +55,7 @@ def _declare(L):
         "ecgb_trainer_run": ([vp, u32, vp, vp, vp, C.POINTER(u32)], i32),
         "ecgb_trainer_length": ([vp, C.POINTER(u64)], i32),
         "ecgb_trainer_ids_host": ([vp, vp, u64, C.POINTER(u64)], i32),
+        "ecgb_trainer_lengths": ([vp, u32, vp], i32),
         "ecgb_trainer_histogram": ([vp, vp, vp, u64, C.POINTER(u64)], i32),
         "ecgb_trainer_dist_sizes": ([vp, C.POINTER(u32), C.POINTER(u32)], i32),
         "ecgb_trainer_dist_begin": ([vp, i32, i32, vp, vp], i32),

@@ -314,6 +314,12 @@ class Trainer:
         check(lib().ecgb_trainer_ids_host(self._h, _np(out), out.size, C.byref(got)))
         return out[: got.value]
 
+    def lengths(self, n_steps):
+        """stream length after 0..n_steps merges (uint64 [n_steps + 1])."""
+        out = np.zeros(int(n_steps) + 1, np.uint64)
+        check(lib().ecgb_trainer_lengths(self._h, int(n_steps), _np(out)))
+        return out
+
     def histogram(self):
         """{(left, right): count} of the live pair histogram."""
         n = C.c_uint64(0)

@@ -162,6 +162,8 @@ int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *h_pairs, ui
 int ecgb_trainer_length(ecgb_trainer *t, uint64_t *n_out);
 int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t cap, uint64_t *n_out);
 
+/* h_n[i] = length of this shard's token stream after i merge steps, i in [0, n_steps] */
+int ecgb_trainer_lengths(ecgb_trainer *t, uint32_t n_steps, uint64_t *h_n);
 /* every pair with a non-zero count in the live histogram (== get_stats, lib.rs:28-48, of
  * the current stream); two-call sizing through *n_out / ECGB_ECAPACITY */
 int ecgb_trainer_histogram(ecgb_trainer *t, uint32_t *h_pairs, int64_t *h_counts, uint64_t cap,

@@ -112,6 +112,8 @@ def test_train_config1_scale_matches_fixture():
     np.testing.assert_array_equal(ntied, f["ntied"])
     ids = tr.ids()
     assert len(ids) == int(f["n_ids"][0])
+    lens = tr.lengths(5000)
+    assert int(lens[0]) == sym.numel() and int(lens[-1]) == len(ids) and np.all(np.diff(lens.astype(np.int64)) < 0)
     crc = np.bitwise_xor.reduce(ids.astype(np.uint64) * (np.arange(len(ids), dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)))
     assert int(crc) == int(f["ids_crc"][0])
     # the live histogram equals a recount of the final stream (get_stats, lib.rs:28-48)
@@ -120,3 +122,36 @@ def test_train_config1_scale_matches_fixture():
     uk, uc = np.unique(keys, return_counts=True)
     want = {(int(k >> np.uint64(32)), int(k & np.uint64(0xFFFFFFFF))): int(c) for k, c in zip(uk, uc)}
     assert h == want
+
+
+def _check_sharded(oracle, text, cuts, m):
+    from ecgbyte.dist_train import train_shards_local
+    text = np.ascontiguousarray(text, np.uint8)
+    bounds = [0] + list(cuts) + [len(text)]
+    shards = [text[bounds[r]:bounds[r + 1]].tobytes() for r in range(len(bounds) - 1)]
+    res, trs = train_shards_local(shards, m)
+    o_ids, o_pairs, o_counts, o_ntied = oracle.train_pairs(text, m, fast=len(text) > 20000)
+    for pairs, counts, ntied in res:  # every rank reports the same merges
+        np.testing.assert_array_equal(pairs, o_pairs)
+        np.testing.assert_array_equal(counts, o_counts)
+        np.testing.assert_array_equal(ntied, o_ntied)
+    ids = np.concatenate([t.ids() for t in trs])
+    np.testing.assert_array_equal(ids, o_ids)
+    assert sum(int(t.lengths(len(o_pairs))[-1]) for t in trs) == len(o_ids)
+
+
+def test_sharded_training_one_gpu_many_ranks(oracle, small_corpus):
+    """The sharded kernels (halos, run parity across shards, delta lists, replicated
+    histogram) driven by several trainers on one GPU == single-string training."""
+    rng = np.random.default_rng(4)
+    text = rng.integers(97, 100, size=5000).astype(np.uint8)
+    _check_sharded(oracle, text, [1700, 3300], 60)
+    _check_sharded(oracle, text, [0, 1, 2, 4999], 40)          # empty and single-token shards
+    runs = np.concatenate([np.full(4100, 105, np.uint8), rng.integers(104, 107, size=50).astype(np.uint8),
+                           np.full(8300, 105, np.uint8), np.array([106, 105, 105], np.uint8)])
+    for cuts in ([4096], [4097, 4150], [100, 4200, 12000], [6000, 6001, 6002]):
+        _check_sharded(oracle, runs, cuts, 16)                  # (x,x) runs across shard and tile edges
+    x, pct = small_corpus
+    sym = oracle.quantize(x[:4], pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    n = sym.size
+    _check_sharded(oracle, sym, [n // 4, n // 2, 3 * n // 4], 300)
