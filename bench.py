@@ -134,9 +134,12 @@ def run_reference(args, rank, world):
     from ecgbyte import synth
     pairs, pct = load_table()
     cores = os.cpu_count() or 1
-    per_step = max(cores * 4, 32)
-    x = synth.corpus(1234, per_step, L_SAMPLES, np.float32)
-    for _ in range(args.warmup):
+    # a step = a bounded sample of the workload: ~3 s of work on all host cores
+    cal = synth.corpus(1234, 4 * cores, L_SAMPLES, np.float32)
+    cal_rate, _, _ = cpu_encode_rate(cal, pct, pairs, cores)
+    per_step = int(min(max(cal_rate * 3.0, 4 * cores), 8192))
+    x = np.concatenate([cal] * ((per_step + len(cal) - 1) // len(cal)))[:per_step]
+    for _ in range(min(args.warmup, 1)):
         cpu_encode_rate(x[: max(cores, 8)], pct, pairs, cores)
     t_tot, n_tot = 0.0, 0
     for _ in range(args.steps):
@@ -287,10 +290,12 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_cpu = int(min(max(cores * 8, 64), 2048))
+        # calibrate on a few records, then time ~12 s of CPU work on records of the same batch
+        cal_rate, _, _ = cpu_encode_rate(x[: 4 * cores].cpu().numpy(), pct, pairs, cores, faithful=True)
+        n_cpu = int(min(max(cal_rate * 12.0, 4 * cores), n_rec, 65536))
         xs_cpu = x[:n_cpu].cpu().numpy()
         rate, dt, _ = cpu_encode_rate(xs_cpu, pct, pairs, cores, faithful=True)
-        rate_am, dt_am, _ = cpu_encode_rate(xs_cpu, pct, pairs, cores, faithful=False)
+        rate_am, dt_am, _ = cpu_encode_rate(xs_cpu[: max(n_cpu // 4, 4 * cores)], pct, pairs, cores, faithful=False)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d records of the same batch in %.1f s; C port of normalize_all + rust_bpe.encode_text "
                          "(trie rebuilt per record as lib.rs:153-161 does); trie built once: %.0f records/s"

@@ -8,7 +8,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 set -x
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches_${TAG}.csv \
+    -k regex:"encode_kernel|quantize_kernel|merge_kernel|argmax_kernel|count_kernel" --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-train --e2e-records 4096 > gpurun_out/launches_${TAG}.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode_kernel -s 3 -c 1 \
     -o gpurun_out/encode_${TAG} -f \
