@@ -24,12 +24,16 @@
 // histogram patches go to a small delta table that is compacted into a list, exchanged
 // with the other ranks (all-gather, by the host) and applied by every rank, so every
 // rank holds the same global histogram and takes the same argmax without a reduction.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace ecgb {
 
@@ -319,11 +323,26 @@ __device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, 
     return h;
 }
 
+struct MergeSmem {
+    Halo halo;
+    long long tile;
+    uint16_t edge[kTPB][6];          // per thread: first 3, last 2 tokens (+pad)
+    long long scan[kTPB / 32];
+    long long lastnon[kTPB / 32];
+    unsigned long long prefix;
+    long long tile_lastnon;
+    uint16_t out[kTile];
+};
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
-__global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
-                                                     PairTable upd) {
-    const Best bb = v.best[step];
-    if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
+__device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
+                                           const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm) {
     const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
     const uint16_t *__restrict__ in = v.tok[step & 1];
     uint16_t *__restrict__ out = v.tok[(step + 1) & 1];
@@ -331,18 +350,10 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
     const long long ntiles = n == 0 ? 1 : (n + kTile - 1) / kTile;
     const bool same = a == b;
 
-    __shared__ Halo s_halo;
-    __shared__ long long s_tile;
-    __shared__ uint16_t s_edge[kTPB][6];          // per thread: first 3, last 2 tokens (+pad)
-    __shared__ long long s_scan[kTPB / 32];
-    __shared__ long long s_lastnon[kTPB / 32];
-    __shared__ unsigned long long s_prefix;
-    __shared__ long long s_tile_lastnon;
-    __shared__ uint16_t s_out[kTile];
-
-    if (threadIdx.x == 0) s_halo = make_halo(all_bd, v.rank, v.world, a, b);
     __syncthreads();
-    const Halo h = s_halo;
+    if (threadIdx.x == 0) sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
+    __syncthreads();
+    const Halo h = sm.halo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // token at global (shard-local) position p, including halo context
@@ -355,9 +366,9 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&v.tickets[step], 1u);
+        if (threadIdx.x == 0) sm.tile = (long long)atomicAdd(&v.tickets[step], 1u);
         __syncthreads();
-        const long long tile = s_tile;
+        const long long tile = sm.tile;
         if (tile >= ntiles) break;
         const long long tbase = tile * kTile;
         const long long base = tbase + (long long)threadIdx.x * kIPT;
@@ -374,23 +385,23 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
 #pragma unroll
             for (int i = 0; i < kIPT; i++) e[2 + i] = (base + i < n) ? (uint32_t)in[base + i] : kSentinel;
         }
-        s_edge[threadIdx.x][0] = (uint16_t)e[2];
-        s_edge[threadIdx.x][1] = (uint16_t)e[3];
-        s_edge[threadIdx.x][2] = (uint16_t)e[4];
-        s_edge[threadIdx.x][3] = (uint16_t)e[2 + kIPT - 2];
-        s_edge[threadIdx.x][4] = (uint16_t)e[2 + kIPT - 1];
+        sm.edge[threadIdx.x][0] = (uint16_t)e[2];
+        sm.edge[threadIdx.x][1] = (uint16_t)e[3];
+        sm.edge[threadIdx.x][2] = (uint16_t)e[4];
+        sm.edge[threadIdx.x][3] = (uint16_t)e[2 + kIPT - 2];
+        sm.edge[threadIdx.x][4] = (uint16_t)e[2 + kIPT - 1];
         __syncthreads();
         if (threadIdx.x > 0) {
-            e[0] = s_edge[threadIdx.x - 1][3];
-            e[1] = s_edge[threadIdx.x - 1][4];
+            e[0] = sm.edge[threadIdx.x - 1][3];
+            e[1] = sm.edge[threadIdx.x - 1][4];
         } else {
             e[0] = tok_at(base - 2);
             e[1] = tok_at(base - 1);
         }
         if (threadIdx.x < kTPB - 1 && base + kIPT + 3 <= n) {
-            e[18] = s_edge[threadIdx.x + 1][0];
-            e[19] = s_edge[threadIdx.x + 1][1];
-            e[20] = s_edge[threadIdx.x + 1][2];
+            e[18] = sm.edge[threadIdx.x + 1][0];
+            e[19] = sm.edge[threadIdx.x + 1][1];
+            e[20] = sm.edge[threadIdx.x + 1][2];
         } else {
             // tile edge or near the end of the shard: positions >= n come from the right halo
             e[18] = tok_at(base + kIPT);
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
                 const long long y = __shfl_up_sync(0xffffffffu, x, o);
                 if (lane >= o) x = max(x, y);
             }
-            if (lane == 31) s_lastnon[warp] = x;
+            if (lane == 31) sm.lastnon[warp] = x;
             // warp 0 additionally scans backwards from the tile start for the run entering the tile
             if (warp == 0) {
                 long long found = -(1ll << 62);
@@ -433,11 +444,11 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
                 }
                 // reached the shard start inside the run: continue it virtually by par_in elements
                 if (!hit) found = -1 - (long long)h.par_in;
-                if (lane == 0) s_tile_lastnon = found;
+                if (lane == 0) sm.tile_lastnon = found;
             }
             __syncthreads();
-            long long before = s_tile_lastnon;  // last non-x position before this thread's range
-            for (int w = 0; w < warp; w++) before = max(before, s_lastnon[w]);
+            long long before = sm.tile_lastnon;  // last non-x position before this thread's range
+            for (int w = 0; w < warp; w++) before = max(before, sm.lastnon[w]);
             const long long xe = __shfl_up_sync(0xffffffffu, x, 1);
             if (lane > 0) before = max(before, xe);
             run_start = before + 1;
@@ -496,47 +507,117 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
             const int y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        if (lane == 31) s_scan[warp] = incl;
+        if (lane == 31) sm.scan[warp] = incl;
         __syncthreads();
         int warp_off = 0, tile_total = 0;
 #pragma unroll
         for (int w = 0; w < kTPB / 32; w++) {
-            const int c = (int)s_scan[w];
+            const int c = (int)sm.scan[w];
             if (w < warp) warp_off += c;
             tile_total += c;
         }
         int o = warp_off + incl - kept;
 #pragma unroll
         for (int i = 0; i < kIPT; i++)
-            if ((keepmask >> i) & 1u) s_out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[2 + i]);
+            if ((keepmask >> i) & 1u) sm.out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[2 + i]);
 
-        // decoupled look-back over the tiles that precede this one
-        if (threadIdx.x == 0) {
+        // decoupled look-back over the tiles that precede this one, 32 tiles per probe (warp 0)
+        if (warp == 0) {
             unsigned long long excl = 0;
             if (tile > 0) {
-                atomicExch(&v.tile_status[tile], pack_status(1, step, (unsigned long long)tile_total));
-                long long j = tile - 1;
+                if (lane == 0) atomicExch(&v.tile_status[tile], pack_status(1, step, (unsigned long long)tile_total));
+                long long j = tile - 1;  // lane l looks at tile j - l
                 for (;;) {
-                    const unsigned long long sdw = atomicAdd(&v.tile_status[j], 0ull);
-                    const uint32_t flag = (uint32_t)(sdw >> 62);
-                    const uint32_t ep = (uint32_t)((sdw >> 42) & 0xFFFFF);
-                    if (flag == 0 || ep != ((step + 1) & 0xFFFFF)) continue;  // not published yet for this step
-                    excl += sdw & kCountMask;
-                    if (flag == 2) break;
-                    j--;
+                    const long long idx = j - lane;
+                    uint32_t flag = 2;            // tiles before the first one: an inclusive prefix of 0
+                    unsigned long long cntv = 0;
+                    if (idx >= 0) {
+                        const unsigned long long sdw = ld_status(&v.tile_status[idx]);
+                        const uint32_t ep = (uint32_t)((sdw >> 42) & 0xFFFFF);
+                        flag = ep == ((step + 1) & 0xFFFFF) ? (uint32_t)(sdw >> 62) : 0u;
+                        cntv = sdw & kCountMask;
+                    }
+                    const unsigned notready = __ballot_sync(0xffffffffu, flag == 0);
+                    const unsigned inclm = __ballot_sync(0xffffffffu, flag == 2);
+                    const int first_nr = notready ? __ffs(notready) - 1 : 32;
+                    const int first_in = inclm ? __ffs(inclm) - 1 : 32;
+                    if (first_in < first_nr) {  // everything up to an inclusive prefix is published
+                        unsigned long long c = lane <= first_in ? cntv : 0ull;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        excl += c;
+                        break;
+                    }
+                    if (first_nr == 32) {  // 32 aggregates: take them all and look further back
+                        unsigned long long c = cntv;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        excl += c;
+                        j -= 32;
+                    }
+                    // else: a needed tile is not published yet -> probe again
                 }
             }
-            __threadfence();
-            atomicExch(&v.tile_status[tile], pack_status(2, step, excl + (unsigned long long)tile_total));
-            s_prefix = excl;
-            if (tile == ntiles - 1) {
-                v.dev->n[(step + 1) & 1] = excl + (unsigned long long)tile_total;
-                v.n_hist[step + 1] = excl + (unsigned long long)tile_total;
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(&v.tile_status[tile], pack_status(2, step, excl + (unsigned long long)tile_total));
+                sm.prefix = excl;
+                if (tile == ntiles - 1) {
+                    v.dev->n[(step + 1) & 1] = excl + (unsigned long long)tile_total;
+                    v.n_hist[step + 1] = excl + (unsigned long long)tile_total;
+                }
             }
         }
         __syncthreads();
-        const unsigned long long gofs = s_prefix;
-        for (int k = threadIdx.x; k < tile_total; k += kTPB) out[gofs + k] = s_out[k];
+        const unsigned long long gofs = sm.prefix;
+        for (int k = threadIdx.x; k < tile_total; k += kTPB) out[gofs + k] = sm.out[k];
+    }
+}
+
+__global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
+                                                     PairTable upd) {
+    __shared__ MergeSmem sm;
+    const Best bb = v.best[step];
+    if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
+    merge_pass(v, step, bb, all_bd, upd, sm);
+}
+
+// The whole single-device training loop (lib.rs:85-117) as ONE persistent cooperative
+// kernel: per step, a grid-wide argmax over the pair table, a grid barrier, the streaming
+// merge pass, a grid barrier.  No launches and no host round trips inside the loop.
+__global__ void __launch_bounds__(kTPB) train_loop_kernel(TrainView v, uint32_t n_steps) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ MergeSmem sm;
+    __shared__ Best s_best;
+    const PairTable &t = v.main;
+    const uint64_t cap = (uint64_t)t.mask + 1;
+    for (uint32_t step = 0; step < n_steps; step++) {
+        Best mine{0, kEmptyKey, 0};
+        for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t k = t.keys[s];
+            if (k == kEmptyKey) continue;
+            const unsigned long long c = t.cnt[s];
+            if (c == 0) continue;
+            mine = better(mine, Best{c, k, 1});
+        }
+        Best bb = block_best(mine);
+        if (threadIdx.x == 0) v.partial[blockIdx.x] = bb;
+        grid.sync();
+        Best p{0, kEmptyKey, 0};
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) p = better(p, v.partial[i]);
+        Best fin = block_best(p);
+        if (threadIdx.x == 0) {
+            s_best = fin;
+            if (blockIdx.x == 0) {
+                v.best[step] = fin;
+                if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+            }
+        }
+        __syncthreads();
+        fin = s_best;
+        if (fin.count == 0) break;  // no pair left (lib.rs:88-90); uniform over the grid
+        merge_pass(v, step, fin, nullptr, v.main, sm);
+        grid.sync();
     }
 }
 
@@ -752,11 +833,17 @@ extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *
     // get_stats once; afterwards the histogram is patched by the merge passes
     count_kernel<<<t->sms * 4, 256, 0, st>>>(t->v.tok[0], n0, kSentinel, t->v.main);
     ECGB_CUDA(cudaGetLastError());
-    const int merge_grid = (int)std::min<uint64_t>((uint64_t)t->sms * 6, n0 / kTile + 1);
-    for (uint32_t step = 0; step < num_merges; step++) {
-        argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
-        merge_kernel<<<merge_grid, kTPB, 0, st>>>(t->v, step, nullptr, t->v.main);
-        if ((step & 255) == 255) ECGB_CUDA(cudaGetLastError());
+    // one persistent cooperative kernel runs every step (grid = all co-resident CTAs)
+    int per_sm = 0;
+    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_loop_kernel, kTPB, 0));
+    if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "train_loop_kernel does not fit on this device");
+    int grid = t->sms * std::min(per_sm, 4);
+    if (grid > kArgmaxBlocks) grid = kArgmaxBlocks;
+    if (num_merges > 0) {
+        TrainView view = t->v;
+        uint32_t steps = num_merges;
+        void *kargs[] = {&view, &steps};
+        ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)train_loop_kernel, dim3(grid), dim3(kTPB), kargs, 0, st));
     }
     ECGB_CUDA(cudaGetLastError());
     ECGB_CUDA(cudaStreamSynchronize(st));
