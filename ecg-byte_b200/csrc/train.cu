@@ -51,6 +51,10 @@ struct PairTable {
     uint32_t mask;             // capacity - 1
     uint32_t *used;            // slots claimed
     uint32_t *overflow;        // set when a probe sequence wrapped
+    // argmax candidates: every slot whose count is >= *tau is listed in cand[0 .. *ncand)
+    // (inbits marks listed slots).  NULL for tables that are never arg-maxed.
+    const unsigned long long *tau;
+    uint32_t *cand, *ncand, *inbits;
 };
 
 struct Best {
@@ -113,7 +117,11 @@ __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long
             if (old == kEmptyKey) { atomicAdd(t.used, 1u); k = key; } else { k = old; }
         }
         if (k == key) {
-            atomicAdd(&t.cnt[slot], (unsigned long long)delta);
+            const unsigned long long old = atomicAdd(&t.cnt[slot], (unsigned long long)delta);
+            if (delta > 0 && t.tau != nullptr && old + (unsigned long long)delta >= *t.tau) {
+                const uint32_t bit = 1u << (slot & 31);
+                if (!(atomicOr(&t.inbits[slot >> 5], bit) & bit)) t.cand[atomicAdd(t.ncand, 1u)] = slot;
+            }
             return;
         }
         slot = (slot + 1) & t.mask;
@@ -121,10 +129,46 @@ __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long
     atomicExch(t.overflow, 1u);
 }
 
+// Block-private patch table: the histogram patches of one merge pass are first folded in
+// shared memory (early merge steps hit a few hundred keys millions of times) and flushed
+// to the global table once per CTA per step.
+constexpr int kPatchSlots = 2048;
+struct PatchTable {
+    uint32_t keys[kPatchSlots];
+    int vals[kPatchSlots];
+};
+
+__device__ __forceinline__ void patch_add(PatchTable &p, const PairTable &t, uint32_t key, int delta) {
+    uint32_t slot = hash_key(key) & (kPatchSlots - 1);
+#pragma unroll 1
+    for (int probes = 0; probes < 16; probes++) {
+        uint32_t k = p.keys[slot];
+        if (k == kEmptyKey) {
+            const uint32_t old = atomicCAS(&p.keys[slot], kEmptyKey, key);
+            k = old == kEmptyKey ? key : old;
+        }
+        if (k == key) {
+            atomicAdd(&p.vals[slot], delta);
+            return;
+        }
+        slot = (slot + 1) & (kPatchSlots - 1);
+    }
+    table_add(t, key, (long long)delta);  // private table crowded: go to the global one
+}
+
+__device__ __forceinline__ void patch_clear(PatchTable &p) {
+    for (int i = threadIdx.x; i < kPatchSlots; i += blockDim.x) { p.keys[i] = kEmptyKey; p.vals[i] = 0; }
+}
+
+__device__ __forceinline__ void patch_flush(PatchTable &p, const PairTable &t) {
+    for (int i = threadIdx.x; i < kPatchSlots; i += blockDim.x)
+        if (p.keys[i] != kEmptyKey && p.vals[i] != 0) table_add(t, p.keys[i], (long long)p.vals[i]);
+}
+
 // All 32 lanes call; lanes with the same key are folded into one atomic.
-__device__ __forceinline__ void warp_table_add(const PairTable &t, bool valid, uint32_t key, long long delta) {
+__device__ __forceinline__ void warp_patch_add(PatchTable &p, const PairTable &t, bool valid, uint32_t key, int delta) {
     const unsigned m = __match_any_sync(0xffffffffu, valid ? key : kEmptyKey);
-    if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) table_add(t, key, delta * (long long)__popc(m));
+    if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) patch_add(p, t, key, delta * __popc(m));
 }
 
 __device__ __forceinline__ uint32_t mk(uint32_t l, uint32_t r) { return (l << 16) | r; }
@@ -326,12 +370,14 @@ __device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, 
 struct MergeSmem {
     Halo halo;
     long long tile;
-    uint16_t edge[kTPB][6];          // per thread: first 3, last 2 tokens (+pad)
     long long scan[kTPB / 32];
     long long lastnon[kTPB / 32];
     unsigned long long prefix;
     long long tile_lastnon;
-    uint16_t out[kTile];
+    // in[2 + q] = token at tile position q; in[0..1] / in[2 + kTile ..] = 2 / 3 tokens of context
+    __align__(16) uint16_t in[kTile + 16];
+    __align__(16) uint16_t out[kTile];
+    PatchTable patch;
 };
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
@@ -341,6 +387,9 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 }
 
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
+// TICKETS: tiles are handed out by an atomic counter (any grid size); otherwise tile =
+// blockIdx + k * gridDim, which needs every block to be co-resident (cooperative launch).
+template <bool TICKETS>
 __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
                                            const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm) {
     const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
@@ -352,11 +401,12 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
 
     __syncthreads();
     if (threadIdx.x == 0) sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
+    patch_clear(sm.patch);
     __syncthreads();
     const Halo h = sm.halo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // token at global (shard-local) position p, including halo context
+    // token at shard-local position p, including halo context
     auto tok_at = [&](long long p) -> uint32_t {
         if (p >= 0 && p < n) return in[p];
         if (p < 0) return (-p <= (long long)h.nl) ? h.L[2 + p] : kSentinel;
@@ -364,76 +414,64 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         return q < (long long)h.nr ? h.R[q] : kSentinel;
     };
 
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sm.tile = (long long)atomicAdd(&v.tickets[step], 1u);
-        __syncthreads();
-        const long long tile = sm.tile;
+    for (long long round = 0;; round++) {
+        long long tile;
+        if (TICKETS) {
+            __syncthreads();
+            if (threadIdx.x == 0) sm.tile = (long long)atomicAdd(&v.tickets[step], 1u);
+            __syncthreads();
+            tile = sm.tile;
+        } else {
+            tile = (long long)blockIdx.x + round * (long long)gridDim.x;
+            __syncthreads();  // shared staging of the previous tile is free again
+        }
         if (tile >= ntiles) break;
         const long long tbase = tile * kTile;
         const long long base = tbase + (long long)threadIdx.x * kIPT;
 
-        // ---- load 16 tokens per thread (sentinel beyond the end) ----
-        uint32_t e[kIPT + 5];  // e[2 + i] = token base + i ; e[0..1] left context ; e[18..20] right context
+        // ---- load 16 tokens per thread into registers and into the shared tile ----
+        uint32_t e[kIPT + 2];  // e[1 + i] = token base + i ; e[0] / e[17] = neighbours
         if (base + kIPT <= n) {
             const uint4 v0 = *reinterpret_cast<const uint4 *>(in + base);
             const uint4 v1 = *reinterpret_cast<const uint4 *>(in + base + 8);
             const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int i = 0; i < 8; i++) { e[2 + 2 * i] = w[i] & 0xFFFFu; e[3 + 2 * i] = w[i] >> 16; }
-        } else {
+            for (int i = 0; i < 8; i++) { e[1 + 2 * i] = w[i] & 0xFFFFu; e[2 + 2 * i] = w[i] >> 16; }
+        } else {  // end of the shard: positions >= n show the right halo (or the sentinel)
 #pragma unroll
-            for (int i = 0; i < kIPT; i++) e[2 + i] = (base + i < n) ? (uint32_t)in[base + i] : kSentinel;
+            for (int i = 0; i < kIPT; i++) e[1 + i] = tok_at(base + i);
         }
-        sm.edge[threadIdx.x][0] = (uint16_t)e[2];
-        sm.edge[threadIdx.x][1] = (uint16_t)e[3];
-        sm.edge[threadIdx.x][2] = (uint16_t)e[4];
-        sm.edge[threadIdx.x][3] = (uint16_t)e[2 + kIPT - 2];
-        sm.edge[threadIdx.x][4] = (uint16_t)e[2 + kIPT - 1];
+        {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = e[1 + 2 * i] | (e[2 + 2 * i] << 16);
+            // in[2 + q]: 4-byte aligned rows -> eight 32-bit stores
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.in[2 + threadIdx.x * kIPT]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) dst[i] = w[i];
+        }
+        if (threadIdx.x < 2) sm.in[threadIdx.x] = (uint16_t)tok_at(tbase - 2 + threadIdx.x);
+        if (threadIdx.x >= 2 && threadIdx.x < 5) sm.in[2 + kTile + threadIdx.x - 2] = (uint16_t)tok_at(tbase + kTile + threadIdx.x - 2);
         __syncthreads();
-        if (threadIdx.x > 0) {
-            e[0] = sm.edge[threadIdx.x - 1][3];
-            e[1] = sm.edge[threadIdx.x - 1][4];
-        } else {
-            e[0] = tok_at(base - 2);
-            e[1] = tok_at(base - 1);
-        }
-        if (threadIdx.x < kTPB - 1 && base + kIPT + 3 <= n) {
-            e[18] = sm.edge[threadIdx.x + 1][0];
-            e[19] = sm.edge[threadIdx.x + 1][1];
-            e[20] = sm.edge[threadIdx.x + 1][2];
-        } else {
-            // tile edge or near the end of the shard: positions >= n come from the right halo
-            e[18] = tok_at(base + kIPT);
-            e[19] = tok_at(base + kIPT + 1);
-            e[20] = tok_at(base + kIPT + 2);
-        }
-        // positions >= n inside this thread's own range must also see the right halo
-        if (base + kIPT > n) {
-#pragma unroll
-            for (int i = 0; i < kIPT; i++)
-                if (base + i >= n) e[2 + i] = tok_at(base + i);
-        }
+        e[0] = sm.in[2 + threadIdx.x * kIPT - 1];
+        e[kIPT + 1] = sm.in[2 + threadIdx.x * kIPT + kIPT];
 
         // ---- (x,x): run offset parity needs the position of the last non-x before each token ----
         long long run_start = 0;  // start of the x-run that is open when this thread's range begins
         if (same) {
-            long long lastnon = -1;  // last position in this thread's range holding a non-x token (LLONG_MIN-ish = none)
+            long long lastnon = -1;
             bool any = false;
 #pragma unroll
             for (int i = 0; i < kIPT; i++)
-                if (base + i < n && e[2 + i] != a) { lastnon = base + i; any = true; }
-            long long val = any ? lastnon : -(1ll << 62);
-            // inclusive max-scan across the block
-            long long x = val;
+                if (base + i < n && e[1 + i] != a) { lastnon = base + i; any = true; }
+            long long x = any ? lastnon : -(1ll << 62);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < 32; o <<= 1) {  // inclusive max-scan inside the warp
                 const long long y = __shfl_up_sync(0xffffffffu, x, o);
                 if (lane >= o) x = max(x, y);
             }
             if (lane == 31) sm.lastnon[warp] = x;
-            // warp 0 additionally scans backwards from the tile start for the run entering the tile
-            if (warp == 0) {
+            if (warp == 0) {  // run entering the tile: scan backwards from the tile start
                 long long found = -(1ll << 62);
                 bool hit = false;
                 for (long long p = tbase - 1; p >= 0 && !hit; p -= 32) {
@@ -447,7 +485,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 if (lane == 0) sm.tile_lastnon = found;
             }
             __syncthreads();
-            long long before = sm.tile_lastnon;  // last non-x position before this thread's range
+            long long before = sm.tile_lastnon;
             for (int w = 0; w < warp; w++) before = max(before, sm.lastnon[w]);
             const long long xe = __shfl_up_sync(0xffffffffu, x, 1);
             if (lane > 0) before = max(before, xe);
@@ -464,41 +502,47 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 const bool valid = p < n;
                 bool st, rm;
                 if (same) {
-                    const bool isa = e[2 + i] == a;
+                    const bool isa = e[1 + i] == a;
                     const bool odd = ((p - rs) & 1) != 0;
-                    st = valid && isa && !odd && e[3 + i] == a;
+                    st = valid && isa && !odd && e[2 + i] == a;
                     rm = valid && isa && odd;
                     if (!isa) rs = p + 1;
                 } else {
-                    st = valid && e[2 + i] == a && e[3 + i] == b;
-                    rm = valid && e[1 + i] == a && e[2 + i] == b;
+                    st = valid && e[1 + i] == a && e[2 + i] == b;
+                    rm = valid && e[i] == a && e[1 + i] == b;
                 }
                 site |= (st ? 1u : 0u) << i;
                 removed |= (rm ? 1u : 0u) << i;
             }
         }
-        // (a != b, first token of the shard): e[1] is the left halo, handled by the general rule.
 
-        // ---- histogram patches at the sites (see oracle/ecgb_oracle.c ecgo_train_fast) ----
+        // ---- histogram patches, one site at a time (see oracle/ecgb_oracle.c ecgo_train_fast) ----
+        {
+            int ns = __popc(site);
 #pragma unroll
-        for (int i = 0; i < kIPT; i++) {
-            const bool st = (site >> i) & 1u;
-            if (!__any_sync(0xffffffffu, st)) continue;
-            const uint32_t tm2 = e[i], tm1 = e[1 + i], tp2 = e[4 + i], tp3 = e[5 + i];
-            const bool has_left = st && tm1 != kSentinel;
-            const bool prev_site = has_left && tm2 == a && tm1 == b;      // site at p-2 (parity is implied)
-            const bool has_right = st && tp2 != kSentinel;
-            const bool next_site = has_right && tp2 == a && tp3 == b;     // site at p+2
-            warp_table_add(upd, st, mk(a, b), -1);
-            warp_table_add(upd, has_left, mk(tm1, a), -1);
-            warp_table_add(upd, has_left, mk(prev_site ? z : tm1, z), +1);
-            warp_table_add(upd, has_right && !next_site, mk(b, tp2), -1);
-            warp_table_add(upd, has_right && !next_site, mk(z, tp2), +1);
+            for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+            if (lane == 0 && ns) patch_add(sm.patch, upd, mk(a, b), -ns);  // the pair itself, per warp
+            const uint16_t *ctx = &sm.in[threadIdx.x * kIPT];  // ctx[2 + i] = token at base + i
+            uint32_t rem = site;
+            while (rem) {
+                const int i = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t tm2 = ctx[i], tm1 = ctx[1 + i], tp2 = ctx[4 + i], tp3 = ctx[5 + i];
+                if (tm1 != kSentinel) {  // there is a left neighbour
+                    const bool prev_site = tm2 == a && tm1 == b;  // site at p-2 (parity is implied)
+                    patch_add(sm.patch, upd, mk(tm1, a), -1);
+                    patch_add(sm.patch, upd, mk(prev_site ? z : tm1, z), +1);
+                }
+                if (tp2 != kSentinel && !(tp2 == a && tp3 == b)) {  // right neighbour that starts no site
+                    patch_add(sm.patch, upd, mk(b, tp2), -1);
+                    patch_add(sm.patch, upd, mk(z, tp2), +1);
+                }
+            }
         }
 
         // ---- compaction: kept tokens -> shared staging -> coalesced stores ----
         uint32_t nvalid = (base >= n) ? 0u : (uint32_t)min((long long)kIPT, n - base);
-        const uint32_t validmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        const uint32_t validmask = (1u << nvalid) - 1u;
         const uint32_t keepmask = validmask & ~removed;
         const int kept = __popc(keepmask);
         int incl = kept;
@@ -519,7 +563,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         int o = warp_off + incl - kept;
 #pragma unroll
         for (int i = 0; i < kIPT; i++)
-            if ((keepmask >> i) & 1u) sm.out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[2 + i]);
+            if ((keepmask >> i) & 1u) sm.out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[1 + i]);
 
         // decoupled look-back over the tiles that precede this one, 32 tiles per probe (warp 0)
         if (warp == 0) {
@@ -544,14 +588,14 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                     if (first_in < first_nr) {  // everything up to an inclusive prefix is published
                         unsigned long long c = lane <= first_in ? cntv : 0ull;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        for (int o2 = 16; o2 > 0; o2 >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o2);
                         excl += c;
                         break;
                     }
                     if (first_nr == 32) {  // 32 aggregates: take them all and look further back
                         unsigned long long c = cntv;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        for (int o2 = 16; o2 > 0; o2 >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o2);
                         excl += c;
                         j -= 32;
                     }
@@ -572,6 +616,8 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         const unsigned long long gofs = sm.prefix;
         for (int k = threadIdx.x; k < tile_total; k += kTPB) out[gofs + k] = sm.out[k];
     }
+    __syncthreads();
+    patch_flush(sm.patch, upd);
 }
 
 __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
@@ -579,44 +625,77 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
     __shared__ MergeSmem sm;
     const Best bb = v.best[step];
     if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
-    merge_pass(v, step, bb, all_bd, upd, sm);
+    merge_pass<true>(v, step, bb, all_bd, upd, sm);
 }
 
 // The whole single-device training loop (lib.rs:85-117) as ONE persistent cooperative
 // kernel: per step, a grid-wide argmax over the pair table, a grid barrier, the streaming
 // merge pass, a grid barrier.  No launches and no host round trips inside the loop.
+// grid-wide fold of per-block partial maxima; every block ends up with the same result
+__device__ __forceinline__ Best grid_best(cg::grid_group &grid, const TrainView &v, Best mine, Best *s_best) {
+    Best bb = block_best(mine);
+    if (threadIdx.x == 0) v.partial[blockIdx.x] = bb;
+    grid.sync();
+    Best p{0, kEmptyKey, 0};
+    for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) p = better(p, v.partial[i]);
+    Best fin = block_best(p);
+    __syncthreads();
+    if (threadIdx.x == 0) *s_best = fin;
+    __syncthreads();
+    fin = *s_best;
+    grid.sync();  // partial[] may be rewritten after this point
+    return fin;
+}
+
 __global__ void __launch_bounds__(kTPB) train_loop_kernel(TrainView v, uint32_t n_steps) {
     cg::grid_group grid = cg::this_grid();
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
     const PairTable &t = v.main;
     const uint64_t cap = (uint64_t)t.mask + 1;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long *tau = const_cast<unsigned long long *>(t.tau);
     for (uint32_t step = 0; step < n_steps; step++) {
+        // ---- argmax (lib.rs:92-94): over the candidate list; every pair whose count is >= tau
+        //      is listed, so a listed maximum >= tau is the global one (with all its ties)
+        const unsigned long long cur_tau = *tau;
+        const uint32_t nc = *t.ncand;
         Best mine{0, kEmptyKey, 0};
-        for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
-            const uint32_t k = t.keys[s];
-            if (k == kEmptyKey) continue;
-            const unsigned long long c = t.cnt[s];
-            if (c == 0) continue;
-            mine = better(mine, Best{c, k, 1});
+        for (uint64_t i = gtid; i < nc; i += gthreads) {
+            const uint32_t slot = t.cand[i];
+            const unsigned long long c = t.cnt[slot];
+            if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
         }
-        Best bb = block_best(mine);
-        if (threadIdx.x == 0) v.partial[blockIdx.x] = bb;
-        grid.sync();
-        Best p{0, kEmptyKey, 0};
-        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) p = better(p, v.partial[i]);
-        Best fin = block_best(p);
-        if (threadIdx.x == 0) {
-            s_best = fin;
-            if (blockIdx.x == 0) {
-                v.best[step] = fin;
-                if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+        Best fin = grid_best(grid, v, mine, &s_best);
+        if (fin.count == 0 || fin.count < cur_tau) {
+            // the list is exhausted: full scan for the true maximum, then rebuild the list with
+            // a lower threshold (counts only decay, so this happens O(log) times per run)
+            mine = Best{0, kEmptyKey, 0};
+            for (uint64_t s = gtid; s < cap; s += gthreads) {
+                const uint32_t k = t.keys[s];
+                if (k == kEmptyKey) continue;
+                const unsigned long long c = t.cnt[s];
+                if (c != 0) mine = better(mine, Best{c, k, 1});
             }
+            fin = grid_best(grid, v, mine, &s_best);
+            const unsigned long long new_tau = fin.count - fin.count / 4 > 0 ? fin.count - fin.count / 4 : 1;
+            if (gtid == 0) { *tau = new_tau; *t.ncand = 0; }
+            for (uint64_t w = gtid; w < (cap + 31) / 32; w += gthreads) t.inbits[w] = 0;
+            grid.sync();
+            for (uint64_t s = gtid; s < cap; s += gthreads) {
+                if (t.keys[s] == kEmptyKey || t.cnt[s] < new_tau) continue;
+                atomicOr(&t.inbits[s >> 5], 1u << (s & 31));
+                t.cand[atomicAdd(t.ncand, 1u)] = (uint32_t)s;
+            }
+            grid.sync();
         }
-        __syncthreads();
-        fin = s_best;
+        if (gtid == 0) {
+            v.best[step] = fin;
+            if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+        }
         if (fin.count == 0) break;  // no pair left (lib.rs:88-90); uniform over the grid
-        merge_pass(v, step, fin, nullptr, v.main, sm);
+        merge_pass<false>(v, step, fin, nullptr, v.main, sm);
         grid.sync();
     }
 }
@@ -674,7 +753,7 @@ struct ecgb_trainer {
     uint32_t argmax_for = 0;   // best[] entries computed so far
     bool loaded = false;
     TrainView v{};
-    void *blocks[16] = {nullptr};
+    void *blocks[32] = {nullptr};
     int n_blocks = 0;
     uint32_t *d_list = nullptr;  // this rank's delta list
 };
@@ -698,6 +777,8 @@ static int alloc_table(ecgb_trainer *t, PairTable *pt, uint32_t log2cap) {
     if ((rc = dev_alloc(t, (void **)&pt->used, 8, true))) return rc;
     pt->overflow = pt->used + 1;
     pt->mask = (uint32_t)(cap - 1);
+    pt->tau = nullptr;
+    pt->cand = pt->ncand = pt->inbits = nullptr;
     cudaError_t e = cudaMemset(pt->keys, 0xFF, cap * 4);
     if (e != cudaSuccess) return fail(ECGB_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     return ECGB_OK;
@@ -728,6 +809,15 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
     if (!rc) rc = dev_alloc(t, (void **)&t->v.dev, sizeof(DevState), true);
     if (!rc) rc = alloc_table(t, &t->v.main, table_log2);
     if (!rc) rc = alloc_table(t, &t->v.delta, 18);
+    if (!rc) {  // argmax candidate list of the main table
+        const size_t cap = (size_t)1 << table_log2;
+        unsigned long long *tau = nullptr;
+        rc = dev_alloc(t, (void **)&t->v.main.cand, cap * 4, false);
+        if (!rc) rc = dev_alloc(t, (void **)&t->v.main.inbits, cap / 8 + 8, true);
+        if (!rc) rc = dev_alloc(t, (void **)&tau, 16, true);
+        t->v.main.tau = tau;
+        t->v.main.ncand = reinterpret_cast<uint32_t *>(tau + 1);
+    }
     if (!rc) rc = dev_alloc(t, (void **)&t->v.best, sizeof(Best) * ((size_t)max_merges + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * kArgmaxBlocks, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tickets, 4 * ((size_t)max_merges + 1), true);
@@ -761,6 +851,10 @@ static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
     ECGB_CUDA(cudaMemsetAsync(t->v.main.keys, 0xFF, cap * 4, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.main.cnt, 0, cap * 8, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.main.used, 0, 8, st));
+    // tau = 2^64 - 1: the first argmax finds an empty candidate list and builds it
+    ECGB_CUDA(cudaMemsetAsync(const_cast<unsigned long long *>(t->v.main.tau), 0xFF, 8, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.main.ncand, 0, 8, st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.main.inbits, 0, cap / 8 + 8, st));
     const size_t dcap = (size_t)t->v.delta.mask + 1;
     ECGB_CUDA(cudaMemsetAsync(t->v.delta.keys, 0xFF, dcap * 4, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.delta.cnt, 0, dcap * 8, st));
