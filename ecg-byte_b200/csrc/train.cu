@@ -662,12 +662,28 @@ __global__ void __launch_bounds__(kTPB) train_loop_kernel(TrainView v, uint32_t 
         const unsigned long long cur_tau = *tau;
         const uint32_t nc = *t.ncand;
         Best mine{0, kEmptyKey, 0};
-        for (uint64_t i = gtid; i < nc; i += gthreads) {
-            const uint32_t slot = t.cand[i];
-            const unsigned long long c = t.cnt[slot];
-            if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+        Best fin;
+        if (nc <= 8 * kTPB) {
+            // short list: block 0 scans it alone, one grid barrier publishes the winner
+            if (blockIdx.x == 0) {
+                for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+                    const uint32_t slot = t.cand[i];
+                    const unsigned long long c = t.cnt[slot];
+                    if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+                }
+                const Best b0 = block_best(mine);
+                if (threadIdx.x == 0) v.partial[kArgmaxBlocks] = b0;
+            }
+            grid.sync();
+            fin = v.partial[kArgmaxBlocks];
+        } else {
+            for (uint64_t i = gtid; i < nc; i += gthreads) {
+                const uint32_t slot = t.cand[i];
+                const unsigned long long c = t.cnt[slot];
+                if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+            }
+            fin = grid_best(grid, v, mine, &s_best);
         }
-        Best fin = grid_best(grid, v, mine, &s_best);
         if (fin.count == 0 || fin.count < cur_tau) {
             // the list is exhausted: full scan for the true maximum, then rebuild the list with
             // a lower threshold (counts only decay, so this happens O(log) times per run)
@@ -819,7 +835,7 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
         t->v.main.ncand = reinterpret_cast<uint32_t *>(tau + 1);
     }
     if (!rc) rc = dev_alloc(t, (void **)&t->v.best, sizeof(Best) * ((size_t)max_merges + 1), true);
-    if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * kArgmaxBlocks, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * (kArgmaxBlocks + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tickets, 4 * ((size_t)max_merges + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tile_status, 8 * ntiles, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
