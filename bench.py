@@ -239,6 +239,9 @@ def run_ours(args, rank, world, local_rank):
         total_tokens_all = int(tt[0])
     else:
         total_tokens_all = total_tokens
+    train_dist = None
+    if world > 1 and not args.no_train:
+        train_dist = bench_train_sharded(dev, pct, rank, world)
     if rank != 0:
         return
 
@@ -314,15 +317,15 @@ def run_ours(args, rank, world, local_rank):
                    "input_dtype": "fp32", "n_merges": int(len(pairs)), "out_stride": stride,
                    "tokens_per_record": total_tokens_all / (world * n_rec), "parallelism": "records sharded x%d" % world,
                    "l2": "inputs (%.1f GB/GPU) exceed L2; no flush" % (n_rec * REC_LEN * 4 / 1e9)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * REC_LEN * 4,
-                "d2h_bytes_per_step": n_e2e * (stride * 4 + 4), "records_per_step": n_e2e, "steps": e2e_steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n_e2e * REC_LEN * 4,
+                "d2h_bytes_per_step": world * n_e2e * (stride * 4 + 4), "records_per_step": world * n_e2e, "steps": e2e_steps,
                 "api": "ecgbyte.api.EncodePipeline.run (pinned host in/out)"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ecgb::encode_kernel<F32>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "cpu_baseline": cpu,
-        "train": train,
+        "train": train if train is not None else train_dist,
         "clocks": clocks,
         "parity": {"records_checked": int(len(idx)), "ok": True},
     }
@@ -358,6 +361,40 @@ def bench_train(dev, pct, peak):
             "corpus_symbols": int(n[0]), "merges": m, "final_tokens": int(n[-1]),
             "algorithmic_bytes": alg, "achieved_gbs": alg / best / 1e9, "frac_of_hbm_peak": alg / best / 1e9 / peak,
             "gpu_launches": 2, "parity": "merge list == oracle fixture (5000 merges)"}
+
+
+def bench_train_sharded(dev, pct, rank, world):
+    """The same corpus cut into `world` contiguous shards, one per rank; two NCCL all-gathers
+    per merge step (ecgbyte/dist_train.py).  Rank 0 checks the merge list against the fixture."""
+    import torch
+    import torch.distributed as dist
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer
+    from ecgbyte.dist_train import split_contiguous, train_shard
+    f = np.load(FIXTURE)
+    x = torch.from_numpy(synth.corpus(0, 1000, L_SAMPLES, np.float32)).to(dev)
+    q = Quantizer(pct, dtype=torch.float32, device=dev)
+    sym = q.quantize(x).reshape(-1)
+    lo, hi = split_contiguous(sym.numel(), world)[rank]
+    shard = sym[lo:hi].contiguous()
+    m = 5000
+    best = None
+    for _ in range(2):
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        pairs, counts, ntied, tr = train_shard(shard, m, device=dev)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        best = float(dt) if best is None else min(best, float(dt))
+    ok = bool(np.array_equal(pairs, f["pairs"].astype(np.uint32)) and np.array_equal(counts, f["counts"]))
+    if not ok:
+        raise SystemExit("bench.py: PARITY FAILURE (sharded merge list differs from the oracle fixture)")
+    return {"metric": "BPE-train merges/sec", "value": m / best, "unit": "merges/s", "seconds": best,
+            "corpus_symbols": int(sym.numel()), "merges": m, "shards": world,
+            "exchange": "2 NCCL all-gathers per merge step (boundary records, histogram delta lists)",
+            "parity": "merge list == oracle fixture (5000 merges)"}
 
 
 def main():
