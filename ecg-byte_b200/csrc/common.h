@@ -71,6 +71,10 @@ struct VocabView {
     const uint32_t *d_wide; // wide nodes (10 words each) when !compact
     int compact;
     int ecg_alphabet;       // class('a'+k) == k for k < 26
+    // decode tables (tokenizer_utils.py:75-77): token id t expands to d_dec_sym[d_dec_off[t] .. d_dec_off[t+1])
+    const uint8_t *d_dec_sym;
+    const uint32_t *d_dec_off;
+    uint32_t dec_ids;       // ids 0 .. dec_ids-1 are covered by d_dec_off
 };
 
 }  // namespace ecgb

@@ -54,6 +54,8 @@ struct ecgb_vocab {
     ecgb::VocabView view{};
     void *d_nodes = nullptr;
     uint8_t *d_cls = nullptr;
+    uint8_t *d_dec_sym = nullptr;
+    uint32_t *d_dec_off = nullptr;
     uint8_t h_cls[256];
     // host copy of the expanded sequences (decode, pickles)
     std::vector<uint32_t> seq;
@@ -208,6 +210,39 @@ extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_of
     v->view.d_cls = v->d_cls;
     v->view.compact = compact ? 1 : 0;
     v->view.ecg_alphabet = 1;  // classes 0..25 are always 'a'..'z' in the compact layout
+
+    // ---- decode tables: id -> expanded bytes (a later merge with the same id wins, like a dict) ----
+    {
+        uint32_t max_id = 255;
+        for (uint32_t i = 0; i < n_merges; i++) max_id = std::max(max_id, h_ids[i]);
+        if (max_id < (1u << 24)) {
+            std::vector<int64_t> which((size_t)max_id + 1, -1);
+            for (uint32_t i = 0; i < n_merges; i++) which[h_ids[i]] = (int64_t)i;
+            std::vector<uint32_t> off((size_t)max_id + 2, 0);
+            std::vector<uint8_t> bytes;
+            for (uint32_t id = 0; id <= max_id; id++) {
+                off[id] = (uint32_t)bytes.size();
+                if (which[id] >= 0) {
+                    const uint64_t o = h_seq_off[which[id]], e2 = h_seq_off[which[id] + 1];
+                    for (uint64_t k = o; k < e2; k++) bytes.push_back((uint8_t)h_seq[k]);
+                } else if (id < 256) {
+                    bytes.push_back((uint8_t)id);
+                }
+            }
+            off[(size_t)max_id + 1] = (uint32_t)bytes.size();
+            cudaError_t e3 = cudaMalloc((void **)&v->d_dec_sym, bytes.size() + 16);
+            if (e3 == cudaSuccess) e3 = cudaMalloc((void **)&v->d_dec_off, off.size() * 4);
+            if (e3 == cudaSuccess) e3 = cudaMemcpy(v->d_dec_sym, bytes.data(), bytes.size(), cudaMemcpyHostToDevice);
+            if (e3 == cudaSuccess) e3 = cudaMemcpy(v->d_dec_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice);
+            if (e3 != cudaSuccess) {
+                ecgb_vocab_destroy(v);
+                return fail(ECGB_ECUDA, "decode table upload failed: %s", cudaGetErrorString(e3));
+            }
+            v->view.d_dec_sym = v->d_dec_sym;
+            v->view.d_dec_off = v->d_dec_off;
+            v->view.dec_ids = max_id + 1;
+        }
+    }
     *out = v;
     return ECGB_OK;
 }
@@ -218,6 +253,8 @@ extern "C" int ecgb_vocab_destroy(ecgb_vocab *v) {
         DeviceGuard g(v->device);
         cudaFree(v->d_nodes);
         cudaFree(v->d_cls);
+        cudaFree(v->d_dec_sym);
+        cudaFree(v->d_dec_off);
     }
     delete v;
     return ECGB_OK;

@@ -20,6 +20,11 @@ class EcgbError(RuntimeError):
         self.status = status
 
 
+class PackCfg(C.Structure):
+    _fields_ = [("pad_id", C.c_int64), ("bos_id", C.c_int64), ("eos_id", C.c_int64), ("sig_start_id", C.c_int64),
+                ("sig_end_id", C.c_int64), ("pad_to_max", C.c_uint32)]
+
+
 class VocabInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_merges", "n_nodes", "n_classes", "compact", "max_token_len", "node_bytes", "smem_nodes", "reserved")]
@@ -48,6 +53,9 @@ def _declare(L):
         "ecgb_encode_batch": ([vp, vp, vp, sz, sz, vp, sz, vp, vp], i32),
         "ecgb_encode_text_host": ([vp, vp, sz, vp, sz, C.POINTER(sz)], i32),
         "ecgb_encode_batch_host": ([vp, vp, vp, sz, sz, vp, sz, vp], i32),
+        "ecgb_decode_symbols": ([vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
+        "ecgb_dequantize": ([dbl, dbl, vp, sz, vp, i32, vp], i32),
+        "ecgb_pack_training": ([vp, sz, vp, sz, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp], i32),
         "ecgb_trainer_create": ([i32, u64, u32, u32, pp], i32),
         "ecgb_trainer_destroy": ([vp], i32),
         "ecgb_trainer_load_device": ([vp, vp, u64, vp], i32),

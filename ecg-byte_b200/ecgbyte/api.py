@@ -193,6 +193,18 @@ class Vocab:
                                            _np(lens)))
         return tokens, lens
 
+    def decode_symbols(self, tokens, lens, sym_stride):
+        """decode_text (tu.py:75-77) for a batch: int32 CUDA tokens [n, stride] + lens [n] ->
+        (uint8 symbols [n, sym_stride], int32 sym_len [n])."""
+        tokens = tokens.contiguous()
+        lens = lens.contiguous()
+        n = tokens.shape[0]
+        sym = torch.empty((n, sym_stride), dtype=torch.uint8, device=tokens.device)
+        sym_len = torch.empty((n,), dtype=torch.int32, device=tokens.device)
+        check(lib().ecgb_decode_symbols(self._h, _ptr(tokens), n, tokens.shape[1], _ptr(lens), _ptr(sym), sym_stride,
+                                        _ptr(sym_len), _stream(tokens.device)))
+        return sym, sym_len
+
     def encode_text(self, text):
         """One string / bytes object -> list[int] (rust_bpe.encode_text semantics)."""
         data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
@@ -212,6 +224,40 @@ class Vocab:
                 self._h = None
         except Exception:
             pass
+
+
+def dequantize(sym, percentiles):
+    """reverse_normalize_all (tu.py:22-28): uint8 CUDA symbols -> float64 CUDA values."""
+    sym = sym.contiguous()
+    out = torch.empty(sym.shape, dtype=torch.float64, device=sym.device)
+    check(lib().ecgb_dequantize(float(percentiles["percentile_1"]), float(percentiles["percentile_99"]), _ptr(sym),
+                                sym.numel(), _ptr(out), sym.device.index, _stream(sym.device)))
+    return out
+
+
+def pack_training(tokens, lens, lut, text, text_off, q_len, pad_to_max, pad_id, bos_id, eos_id, sig_start_id, sig_end_id):
+    """ECGTokenDataset post-processing (data_loader.py:80, 101-132) for a batch on the device.
+    tokens int32 [n, stride], lens int32 [n] (encoder output); lut int64 [256 + M] = LLM id of
+    'signal_k'; text int64 flat question+answer ids, text_off int64 [n + 1], q_len int32 [n].
+    Returns (input_ids, attn_mask, labels, position_ids, status), rows of pad_to_max + 4."""
+    dev = tokens.device
+    n = tokens.shape[0]
+    P = int(pad_to_max) + 4
+    ids = torch.empty((n, P), dtype=torch.int64, device=dev)
+    attn = torch.empty((n, P), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, P), dtype=torch.int64, device=dev)
+    pos = torch.empty((n, P), dtype=torch.int64, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    cfg = _lib.PackCfg(int(pad_id), int(bos_id), int(eos_id), int(sig_start_id), int(sig_end_id), int(pad_to_max))
+    tokens, lens = tokens.contiguous(), lens.contiguous()
+    lut = lut.to(device=dev, dtype=torch.int64).contiguous()
+    text = text.to(device=dev, dtype=torch.int64).contiguous()
+    text_off = text_off.to(device=dev, dtype=torch.int64).contiguous()
+    q_len = q_len.to(device=dev, dtype=torch.int32).contiguous()
+    check(lib().ecgb_pack_training(_ptr(tokens), tokens.shape[1], _ptr(lens), n, _ptr(lut), lut.numel(), _ptr(text),
+                                   _ptr(text_off), _ptr(q_len), C.byref(cfg), _ptr(ids), _ptr(attn), _ptr(labels),
+                                   _ptr(pos), _ptr(status), dev.index, _stream(dev)))
+    return ids, attn, labels, pos, status
 
 
 class EncodePipeline:

@@ -50,11 +50,10 @@ def normalize_all(signal, percentiles):
 
 def reverse_normalize_all(symbol_signal, percentiles):
     """tu.py:22-28 (note: divides by len(ALPHABET) - 1 = 25, as the reference does)."""
-    min_vals = percentiles["percentile_1"] - 0.5
-    max_vals = percentiles["percentile_99"] + 0.5
+    from .api import dequantize
     arr = np.asarray(symbol_signal)
-    codes = arr.astype("S1").view(np.uint8).reshape(arr.shape).astype(np.float64) - 97.0
-    return codes / (len(ALPHABET) - 1) * (max_vals - min_vals) + min_vals
+    codes = np.ascontiguousarray(arr.astype("S1").view(np.uint8).reshape(arr.shape))
+    return dequantize(torch.from_numpy(codes).cuda(), percentiles).cpu().numpy()
 
 
 def process_ecg(ecg, percentiles):

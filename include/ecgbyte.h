@@ -134,6 +134,39 @@ int ecgb_encode_batch_host(const ecgb_vocab *v, const ecgb_quantizer *q, const v
                            int32_t *h_len);
 
 /* ------------------------------------------------------------------------- */
+/* Either side of the encoder                                  */
+/* ------------------------------------------------------------------------- */
+/* decode_text (tokenizer_utils.py:75-77): every token of record r (d_tokens[r*in_stride ..],
+ * d_len[r] of them) is replaced by its expanded bytes; d_sym_len[r] = bytes produced
+ * (bytes beyond sym_stride are counted, not stored).  Synchronises the stream; an id that is
+ * not in the vocabulary gives ECGB_EINVAL (the reference raises KeyError). */
+int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens, size_t n_rec, size_t in_stride,
+                        const int32_t *d_len, uint8_t *d_sym, size_t sym_stride, int32_t *d_sym_len,
+                        void *stream);
+/* reverse_normalize_all (tokenizer_utils.py:22-28): value = (symbol_index / 25) * ((p99+0.5) -
+ * (p1-0.5)) + (p1-0.5) in float64, in that order (note 25 = len(ALPHABET) - 1, as the reference) */
+int ecgb_dequantize(double p1, double p99, const uint8_t *d_sym, size_t n, double *d_out, int device,
+                    void *stream);
+
+/* ECGTokenDataset post-processing (data_loader.py:80, 26-31, 101-132), one row per sample:
+ *   row = [pad]*k + [bos, sig_start] + lut[signal tokens][:available] + [sig_end] + question +
+ *         answer + [eos],  available = pad_to_max - len(question) - len(answer),
+ *   row length pad_to_max + 4; labels are -100 up to the end of the question; attention mask
+ *   0 on pad; position ids = cumsum(mask) - 1 (0 on pad).
+ * d_lut[k] is the LLM id of the string 'signal_k' (main.py:144-146); question+answer ids of
+ * sample r are d_text[d_text_off[r] .. d_text_off[r+1]) with the first d_q_len[r] the question.
+ * d_status[r] = 1 when question+answer exceed pad_to_max (the reference's assert fails there). */
+typedef struct {
+    int64_t pad_id, bos_id, eos_id, sig_start_id, sig_end_id;
+    uint32_t pad_to_max;
+} ecgb_pack_cfg;
+int ecgb_pack_training(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec,
+                       const int64_t *d_lut, uint32_t lut_size, const int64_t *d_text,
+                       const uint64_t *d_text_off, const int32_t *d_q_len, const ecgb_pack_cfg *cfg,
+                       int64_t *d_input_ids, float *d_attn_mask, int64_t *d_labels,
+                       int64_t *d_position_ids, int32_t *d_status, int device, void *stream);
+
+/* ------------------------------------------------------------------------- */
 /* T1-T4  byte_pair_encoding  (lib.rs:58-125)                                */
 /* ------------------------------------------------------------------------- */
 /* The corpus is ONE string (tokenizer_utils.py:93): pairs are counted and merged

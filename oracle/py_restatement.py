@@ -125,3 +125,51 @@ def encode_text(text, merges):
 
 def decode_text(encoded_ids, vocab):
     return "".join(vocab[i] for i in encoded_ids)
+
+
+# ---------------------------------------------------------------------------
+# rows either side of the encoder
+# ---------------------------------------------------------------------------
+def reverse_normalize_all(symbol_codes, p1, p99):
+    """tokenizer_utils.py:22-28 on uint8 symbol codes ('a'..'z')."""
+    min_vals = p1 - 0.5
+    max_vals = p99 + 0.5
+    scaled = np.asarray(symbol_codes).astype(np.int64) - 97
+    clipped = scaled / (len(ALPHABET) - 1)
+    return clipped * (max_vals - min_vals) + min_vals
+
+
+def decode_symbols(tokens, merges):
+    """decode_text (tokenizer_utils.py:75-77) as bytes: concatenation of each token's sequence."""
+    table = {i: [i] for i in range(256)}
+    for seq, tid in merges:
+        table[tid] = list(seq)
+    out = []
+    for t in tokens:
+        out.extend(table[int(t)])
+    return np.array(out, np.uint8)
+
+
+def prepare_training(signal_ids, question, answer, pad_to_max, pad_id, bos_id, eos_id, sig_start_id, sig_end_id):
+    """data_loader.py:26-31 and 101-132 (ECGTokenDataset._prepare_training) in plain Python.
+    signal_ids are already LLM ids (data_loader.py:80).  Returns (input_ids, attn_mask, labels, position_ids)."""
+    sig = list(signal_ids)
+    qa_len = len(question) + len(answer)
+    available = pad_to_max - qa_len
+    if available < 0:
+        raise AssertionError("question + answer longer than pad_to_max")
+    if len(sig) > available:
+        sig = [bos_id, sig_start_id] + sig[:available] + [sig_end_id]
+    elif len(sig) < available:
+        sig = [pad_id] * (available - len(sig)) + [bos_id, sig_start_id] + sig + [sig_end_id]
+    else:
+        sig = [bos_id, sig_start_id] + sig + [sig_end_id]
+    sample = sig + list(question) + list(answer) + [eos_id]
+    labels = [-100] * (len(sig) + len(question)) + list(answer) + [eos_id]
+    mask = [0 if t == pad_id else 1 for t in sample]
+    pos, run = [], 0
+    for m in mask:
+        run += m
+        pos.append(run - 1 if m else 0)
+    assert len(sample) == pad_to_max + 4
+    return (np.array(sample, np.int64), np.array(mask, np.float32), np.array(labels, np.int64), np.array(pos, np.int64))
