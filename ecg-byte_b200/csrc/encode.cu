@@ -309,9 +309,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
                 if (active && base == root_base && pos32 >= end32) avail = 0u;
             }
             uint32_t K = __reduce_min_sync(FULL, avail);
+            // The symbol of the next step is loaded one step ahead (ring[pos + 1], speculating on a
+            // match) and the symbol at the restart point is remembered when a terminal is passed, so
+            // no shared-memory load sits on the step-to-step dependency chain.
+            uint32_t c = lds_u8(ring_addr<R>(ring, pos32));  // symbol at pos32
+            uint32_t cm = lds_u8(ring_addr<R>(ring, mpos));  // symbol at mpos
 #pragma unroll 2
             for (; K > 0; K--) {
-                const uint32_t c = lds_u8(ring_addr<R>(ring, pos32));
+                const int32_t adv = pos32 + 1;
+                const uint32_t cspec = lds_u8(ring_addr<R>(ring, adv));
                 const uint32_t bit = 1u << c;  // the sentinel (31) never has an edge
                 const bool okm = (mask & bit) != 0;
                 // a failed step re-reads the root, which is also the state a new token starts from
@@ -321,9 +327,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
                 if (emit && cnt < stride) outp[cnt] = (int32_t)mid;
                 cnt += emit ? 1u : 0u;
                 const uint32_t tok1 = nd.y & 0xFFFFu;  // token id + 1, 0 = not a token
-                const int32_t adv = pos32 + 1;
-                if (okm && tok1 != 0u) { mpos = adv; mid = tok1 - 1u; }
+                if (okm && tok1 != 0u) { mpos = adv; mid = tok1 - 1u; cm = cspec; }
                 pos32 = okm ? adv : mpos;  // at the root mpos == pos32: a parked walker stays put
+                c = okm ? cspec : cm;
                 mask = nd.x;
                 base = nd.y >> 16;
             }

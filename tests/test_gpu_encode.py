@@ -113,3 +113,52 @@ def test_roundtrip_decode(oracle, small_corpus, small_table):
     ids = tu.encode_text(s, merges)
     assert tu.decode_text(ids, vocab) == s  # train_tokenizer.py:58-60
     assert ids == oracle.encode_text(s, merges)
+
+
+def test_encode_large_vocab_partial_smem(oracle):
+    """A vocabulary whose trie (53k nodes = 430 KB) does not fit in shared memory: the leading
+    nodes are staged, the rest is read through L1/L2 (ALL_SMEM = false path)."""
+    import itertools
+    from ecgbyte.api import Quantizer, Vocab
+    letters = list(range(97, 123))
+    seqs = [list(p) for p in itertools.product(letters, repeat=2)]
+    seqs += [list(p) for p in itertools.product(letters, repeat=3)]
+    seqs += [[f] + list(p) for f in (97, 98) for p in itertools.product(letters, repeat=3)]
+    merges = [(s, 256 + i) for i, s in enumerate(seqs)]
+    v = Vocab(merges=merges)
+    info = v.info()
+    assert info["compact"] == 1 and info["n_nodes"] > 50000
+    trie = oracle.Trie(merges=merges)
+    rng = np.random.default_rng(12)
+    sym = rng.integers(97, 123, size=(40, 3000)).astype(np.uint8)
+    sym[:, ::7] = 97  # plenty of a/b-led 4-grams
+    _check_batch(oracle, v, trie, sym)
+    # fused path with the same vocabulary
+    x = rng.normal(0.3, 0.4, size=(8, 12, 250)).astype(np.float32)
+    pct = {"percentile_1": -0.2, "percentile_99": 0.9}
+    q = Quantizer(pct)
+    s2 = oracle.quantize(x, -0.2, 0.9).reshape(8, -1)
+    w_tok, w_len = trie.encode_batch(s2)
+    tok, lens = v.encode_batch(q, torch.from_numpy(x).cuda())
+    np.testing.assert_array_equal(lens.cpu().numpy(), w_len.astype(np.int32))
+    for r in range(8):
+        np.testing.assert_array_equal(tok[r, : w_len[r]].cpu().numpy(), w_tok[r, : w_len[r]].astype(np.int32))
+
+
+def test_encode_many_records_multiple_passes(oracle, small_table):
+    """More records than walkers (CTAs loop over their range) and out_stride truncation."""
+    from ecgbyte.api import Vocab
+    _, _, merges = small_table
+    v = Vocab(merges=merges)
+    trie = oracle.Trie(merges=merges)
+    rng = np.random.default_rng(13)
+    n = 148 * 768 + 1000
+    sym = rng.integers(104, 108, size=(n, 48)).astype(np.uint8)
+    tok, lens = v.encode_symbols(torch.from_numpy(sym).cuda(), out_stride=8)
+    tok, lens = tok.cpu().numpy(), lens.cpu().numpy()
+    idx = rng.choice(n, size=300, replace=False)
+    w_tok, w_len = trie.encode_batch(sym[idx])
+    np.testing.assert_array_equal(lens[idx], w_len.astype(np.int32))   # true counts even when truncated
+    for k, r in enumerate(idx):
+        m = min(8, w_len[k])
+        np.testing.assert_array_equal(tok[r, :m], w_tok[k, :m].astype(np.int32))
