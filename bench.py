@@ -229,6 +229,29 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = e0.elapsed_time(e1)
     assert np.array_equal(len_h.numpy(), lens_h[:n_e2e].astype(np.int32)), "e2e lengths differ from device-resident run"
 
+    # informational: the same pipeline fed with int16 records (1 uV/LSB, PTB-XL's native type):
+    # half the PCIe bytes per record
+    e2e_i16 = None
+    if not args.no_i16:
+        q16 = Quantizer(pct, dtype=torch.int16, device=dev)
+        x16 = torch.clamp(torch.round(x[:n_e2e] * 1000.0), -32768, 32767).to(torch.int16)
+        xh16 = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.int16).pin_memory()
+        xh16.copy_(x16)
+        pipe16 = EncodePipeline(v, q16, REC_LEN, stride, chunk=args.e2e_chunk)
+        pipe16.run(xh16, tok_h, len_h)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(e2e_steps):
+            pipe16.run(xh16, tok_h, len_h)
+        f1.record()
+        barrier()
+        e2e_i16 = n_e2e * e2e_steps / (f0.elapsed_time(f1) * 1e-3)
+        del x16, xh16, pipe16
+        # restore the fp32 results in the pinned buffers for the parity gate below
+        pipe.run(xh, tok_h, len_h)
+        torch.cuda.synchronize(dev)
+
     # ---- max over ranks ----
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -319,7 +342,8 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (%.1f GB/GPU) exceed L2; no flush" % (n_rec * REC_LEN * 4 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n_e2e * REC_LEN * 4,
                 "d2h_bytes_per_step": world * n_e2e * (stride * 4 + 4), "records_per_step": world * n_e2e, "steps": e2e_steps,
-                "api": "ecgbyte.api.EncodePipeline.run (pinned host in/out)"},
+                "api": "ecgbyte.api.EncodePipeline.run (pinned host in/out)",
+                "int16_input_records_per_s_per_gpu": e2e_i16},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ecgb::encode_kernel<F32>", "kernel_ms": k_ms,
@@ -410,6 +434,7 @@ def main():
     ap.add_argument("--check", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-i16", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

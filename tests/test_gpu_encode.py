@@ -162,3 +162,50 @@ def test_encode_many_records_multiple_passes(oracle, small_table):
     for k, r in enumerate(idx):
         m = min(8, w_len[k])
         np.testing.assert_array_equal(tok[r, :m], w_tok[k, :m].astype(np.int32))
+
+
+def test_full_size_roundtrip_100k_records():
+    """BASELINE.json config 2 at full size (100k records x 12 x 5000 fp32 = 24 GB, 5,000-merge
+    table), checked through size-independent properties on the device:
+      decode(encode(x)) == quantise(x) for every record, token counts consistent, and the fused
+      encoder == quantise-then-encode-symbols; plus a 32-record sample against the CPU oracle."""
+    import os
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Vocab
+    from oracle import oracle as O
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~45 GB of device memory")
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptbxl_1000_m5000.npz"))
+    pct = {"percentile_1": f["pct"][0], "percentile_99": f["pct"][1]}
+    pairs = f["pairs"].astype(np.uint32)
+    v = Vocab.from_pairs(pairs)
+    q = Quantizer(pct, dtype=torch.float32)
+    n, stride = 100000, 8192
+    x = synth.corpus_cuda(77, n, 5000, torch.float32, "cuda:0")
+    tok, lens = v.encode_batch(q, x, out_stride=stride)
+    assert int(lens.max()) <= stride and int(lens.min()) > 0
+    total_sym = 0
+    for c0 in range(0, n, 20000):   # chunked to bound the symbol buffers
+        sl = slice(c0, c0 + 20000)
+        sym = q.quantize(x[sl]).reshape(20000, -1)
+        dec, dec_len = v.decode_symbols(tok[sl], lens[sl], sym.shape[1])
+        assert bool((dec_len == sym.shape[1]).all())
+        assert torch.equal(dec, sym)
+        t2, l2 = v.encode_symbols(sym, out_stride=stride)
+        assert torch.equal(l2, lens[sl])
+        m = torch.arange(stride, device="cuda").unsqueeze(0) < l2.unsqueeze(1)
+        assert torch.equal(torch.where(m, t2, 0), torch.where(m, tok[sl], 0))
+        total_sym += int(dec_len.sum())
+    assert total_sym == n * 60000
+    # every token id is a valid vocabulary id
+    m_all = torch.arange(stride, device="cuda").unsqueeze(0) < lens.unsqueeze(1)
+    assert int(torch.where(m_all, tok, 0).max()) < 256 + len(pairs)
+    idx = np.random.default_rng(1).choice(n, size=32, replace=False)
+    seq, off = O.expand(pairs)
+    trie = O.Trie(flat=(seq, off, np.arange(256, 256 + len(pairs), dtype=np.uint32)))
+    xs = x[torch.from_numpy(idx).cuda()].cpu().numpy()
+    w_tok, w_len = trie.encode_batch(O.quantize(xs, pct["percentile_1"], pct["percentile_99"]).reshape(32, -1), stride)
+    g_tok, g_len = tok[torch.from_numpy(idx).cuda()].cpu().numpy(), lens[torch.from_numpy(idx).cuda()].cpu().numpy()
+    np.testing.assert_array_equal(g_len, w_len.astype(np.int32))
+    for k in range(32):
+        np.testing.assert_array_equal(g_tok[k, : w_len[k]], w_tok[k, : w_len[k]].astype(np.int32))
