@@ -335,9 +335,11 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64-exact threshold classification (fp32 in) + u16/int32 trie walk", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "records_per_gpu": n_rec, "leads": C_LEADS, "samples_per_lead": L_SAMPLES,
                    "input_dtype": "fp32", "n_merges": int(len(pairs)), "out_stride": stride,
+                   "arithmetic": "fp32 threshold classification, bit-identical to the reference's float64 expression; "
+                                 "u8 symbols, 8-byte trie nodes, int32 tokens",
                    "tokens_per_record": total_tokens_all / (world * n_rec), "parallelism": "records sharded x%d" % world,
                    "l2": "inputs (%.1f GB/GPU) exceed L2; no flush" % (n_rec * REC_LEN * 4 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n_e2e * REC_LEN * 4,
