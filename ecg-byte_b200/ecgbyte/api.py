@@ -226,6 +226,32 @@ class Vocab:
             pass
 
 
+def minmax(x):
+    """np.min / np.max of a CUDA tensor (float32 / float64 / int16), NaN propagates."""
+    x = x.contiguous()
+    lo, hi = C.c_double(0), C.c_double(0)
+    check(lib().ecgb_minmax(_ptr(x), _DT[x.dtype], x.numel(), C.byref(lo), C.byref(hi), x.device.index, _stream(x.device)))
+    return lo.value, hi.value
+
+
+def percentiles(samples, q):
+    """np.percentile(samples, q) (method 'linear') for a float64 CUDA tensor of samples."""
+    s = samples.to(torch.float64).contiguous()
+    qs = np.ascontiguousarray(np.atleast_1d(q), np.float64)
+    out = np.zeros(qs.size, np.float64)
+    check(lib().ecgb_percentiles(_ptr(s), s.numel(), _np(qs), qs.size, _np(out), s.device.index, _stream(s.device)))
+    return out
+
+
+def global_stats(segments, samples, skipped_instances=0):
+    """The stats dict of compute_global_stats (preprocess_utils.py:168-213): min / max over all stored
+    samples of `segments`, 1st / 99th percentile of `samples` (the reference draws ~100k of them)."""
+    lo, hi = minmax(segments)
+    p = percentiles(samples, [1, 99])
+    return {"global_min": np.float64(lo), "global_max": np.float64(hi), "percentile_1": np.float64(p[0]),
+            "percentile_99": np.float64(p[1]), "skipped_instances": skipped_instances}
+
+
 def dequantize(sym, percentiles):
     """reverse_normalize_all (tu.py:22-28): uint8 CUDA symbols -> float64 CUDA values."""
     sym = sym.contiguous()

@@ -148,6 +148,15 @@ int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens, size_t n_r
 int ecgb_dequantize(double p1, double p99, const uint8_t *d_sym, size_t n, double *d_out, int device,
                     void *stream);
 
+/* compute_global_stats (preprocess_utils.py:168-213), the step that produces the percentiles
+ * the quantiser consumes: np.min / np.max over every stored sample (NaN propagates) ... */
+int ecgb_minmax(const void *d_in, ecgb_dtype dtype, size_t n, double *h_min, double *h_max, int device,
+                void *stream);
+/* ... and np.percentile(samples, q) with NumPy's default 'linear' method (preprocess_utils.py:205-206)
+ * for nq percentiles at once; d_samples are float64 on the device.  Synchronises the stream. */
+int ecgb_percentiles(const double *d_samples, size_t n, const double *h_q, int nq, double *h_out, int device,
+                     void *stream);
+
 /* ECGTokenDataset post-processing (data_loader.py:80, 26-31, 101-132), one row per sample:
  *   row = [pad]*k + [bos, sig_start] + lut[signal tokens][:available] + [sig_end] + question +
  *         answer + [eos],  available = pad_to_max - len(question) - len(answer),

@@ -104,3 +104,35 @@ def test_batcher_end_to_end(oracle, small_corpus, small_table):
         np.testing.assert_array_equal(out["attn_mask"][r].cpu().numpy(), w[1])
         np.testing.assert_array_equal(out["quantized_signal_ids_input"][r].cpu().numpy(), w[2])
         np.testing.assert_array_equal(out["position_ids"][r].cpu().numpy(), w[3])
+
+
+def test_global_stats_match_numpy(small_corpus):
+    """compute_global_stats' arithmetic (preprocess_utils.py:183-206): np.min / np.max over the segments and
+    np.percentile(samples, 1 / 99) -- NumPy is the reference's own implementation of these."""
+    from ecgbyte.api import global_stats, minmax, percentiles
+    rng = np.random.default_rng(21)
+    x, _ = small_corpus
+    for dt in (np.float64, np.float32):
+        seg = x.astype(dt)
+        lo, hi = minmax(torch.from_numpy(seg).cuda())
+        assert lo == float(seg.min()) and hi == float(seg.max())
+    xi = rng.integers(-30000, 30000, size=100001).astype(np.int16)
+    assert minmax(torch.from_numpy(xi).cuda()) == (float(xi.min()), float(xi.max()))
+    for n in (1, 2, 3, 100, 100000, 100003):
+        s = rng.normal(0.2, 0.7, size=n)
+        if n > 50:
+            s[::17] = s[5]          # ties
+        qs = [0, 1, 25, 50, 99, 100, 33.3]
+        got = percentiles(torch.from_numpy(s).cuda(), qs)
+        want = np.percentile(s, qs)
+        np.testing.assert_array_equal(got, want)      # bit-exact float64
+    # the reference's sample: all values of the first segments, then a random subset (pu.py:190-195)
+    flat = x.reshape(-1)
+    sample = np.concatenate([flat[:90000], rng.choice(flat[90000:120000], 10000, replace=False)])
+    st = global_stats(torch.from_numpy(x).cuda(), torch.from_numpy(sample).cuda())
+    assert st["percentile_1"] == np.percentile(sample, 1) and st["percentile_99"] == np.percentile(sample, 99)
+    assert st["global_min"] == x.min() and st["global_max"] == x.max()
+    # NaN propagates like np.min / np.percentile
+    bad = s.copy(); bad[7] = np.nan
+    assert np.isnan(percentiles(torch.from_numpy(bad).cuda(), [1])[0])
+    assert all(np.isnan(v) for v in minmax(torch.from_numpy(bad).cuda()))
