@@ -71,6 +71,7 @@ struct VocabView {
     const uint32_t *d_wide; // wide nodes (10 words each) when !compact
     int compact;
     int ecg_alphabet;       // class('a'+k) == k for k < 26
+    uint32_t max_token_len;
     // decode tables (tokenizer_utils.py:75-77): token id t expands to d_dec_sym[d_dec_off[t] .. d_dec_off[t+1])
     const uint8_t *d_dec_sym;
     const uint32_t *d_dec_off;
@@ -89,4 +90,7 @@ struct ecgb_quantizer {
 };
 
 const ecgb::VocabView *ecgb_vocab_view(const ecgb_vocab *v);
+// one long string, parallel over positions (encode_long.cu); compact vocabularies, n < 2^32
+int ecgb_encode_long_device(const ecgb_vocab *v, const uint8_t *d_text, size_t n, uint32_t *d_out, size_t cap,
+                            unsigned long long *h_count, cudaStream_t st);
 int ecgb_vocab_device(const ecgb_vocab *v);

@@ -487,6 +487,7 @@ extern "C" int ecgb_encode_text_host(const ecgb_vocab *v, const uint8_t *h_text,
     if (n == 0) return ECGB_OK;
     ECGB_REQUIRE(h_text, "h_text is NULL");
     int device = ecgb_vocab_device(v);
+    const VocabView *vv = ecgb_vocab_view(v);
     DeviceGuard g(device);
     uint8_t *d_text = nullptr; int32_t *d_tok = nullptr; int32_t *d_len = nullptr;
     const size_t stride = std::min(cap, n);
@@ -494,17 +495,26 @@ extern "C" int ecgb_encode_text_host(const ecgb_vocab *v, const uint8_t *h_text,
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_tok, std::max<size_t>(stride, 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_len, 4);
     int rc = ECGB_OK;
-    int32_t len = 0;
+    unsigned long long count = 0;
     if (e == cudaSuccess) e = cudaMemcpy(d_text, h_text, n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) rc = ecgb_encode_symbols(v, d_text, 1, n, nullptr, d_tok, stride, d_len, nullptr);
-    if (e == cudaSuccess && rc == ECGB_OK) e = cudaMemcpy(&len, d_len, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        if (vv->compact && n >= 4096 && n < 0xFFFFFFF0ull && vv->max_token_len < 0xFFFFu) {
+            // one long string: parallel over positions instead of one walker
+            rc = ecgb_encode_long_device(v, d_text, n, reinterpret_cast<uint32_t *>(d_tok), stride, &count, 0);
+        } else {
+            int32_t len = 0;
+            rc = ecgb_encode_symbols(v, d_text, 1, n, nullptr, d_tok, stride, d_len, nullptr);
+            if (rc == ECGB_OK) e = cudaMemcpy(&len, d_len, 4, cudaMemcpyDeviceToHost);
+            count = (unsigned long long)len;
+        }
+    }
     if (e == cudaSuccess && rc == ECGB_OK && h_out && stride)
-        e = cudaMemcpy(h_out, d_tok, std::min<size_t>((size_t)len, stride) * 4, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(h_out, d_tok, std::min<size_t>((size_t)count, stride) * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_text); cudaFree(d_tok); cudaFree(d_len);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? ECGB_ENOMEM : ECGB_ECUDA, "encode_text_host: %s", cudaGetErrorString(e));
     if (rc) return rc;
-    *n_out = (size_t)len;
-    if ((size_t)len > cap) return fail(ECGB_ECAPACITY, "output capacity %zu < %d tokens", cap, len);
+    *n_out = (size_t)count;
+    if ((size_t)count > cap) return fail(ECGB_ECAPACITY, "output capacity %zu < %llu tokens", cap, count);
     return ECGB_OK;
 }
 

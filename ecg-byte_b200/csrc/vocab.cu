@@ -210,6 +210,7 @@ extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_of
     v->view.d_cls = v->d_cls;
     v->view.compact = compact ? 1 : 0;
     v->view.ecg_alphabet = 1;  // classes 0..25 are always 'a'..'z' in the compact layout
+    v->view.max_token_len = t.max_len;
 
     // ---- decode tables: id -> expanded bytes (a later merge with the same id wins, like a dict) ----
     {

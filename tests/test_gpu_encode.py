@@ -209,3 +209,25 @@ def test_full_size_roundtrip_100k_records():
     np.testing.assert_array_equal(g_len, w_len.astype(np.int32))
     for k in range(32):
         np.testing.assert_array_equal(g_tok[k, : w_len[k]], w_tok[k, : w_len[k]].astype(np.int32))
+
+
+def test_long_string_position_parallel(oracle, small_corpus, small_table):
+    """rust_bpe.encode_text on long strings takes the position-parallel path (encode_long.cu);
+    it must equal the sequential greedy longest match."""
+    import rust_bpe
+    x, pct = small_corpus
+    _, vocab, merges = small_table
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    rng = np.random.default_rng(3)
+    cases = [sym[:4096], sym[:4097], sym[:60000], sym,                       # ECG text, chunk edges, whole corpus
+             np.full(70001, 105, np.uint8),                                   # one run: tokens longer than walks
+             rng.integers(97, 123, size=50000).astype(np.uint8)]              # incompressible
+    mixed = sym[:30000].copy()
+    mixed[::97] = 45                                                          # bytes that occur in no merge
+    cases.append(mixed)
+    trie = oracle.Trie(merges=merges)
+    for s in cases:
+        got = rust_bpe.encode_text(s.tobytes().decode("latin1") if s.max() < 128 else None, merges)
+        want = trie.encode(s)
+        assert len(got) == len(want)
+        np.testing.assert_array_equal(np.array(got, np.uint32), want)
