@@ -93,7 +93,7 @@ struct TrainView {
     Best *best;               // [max_merges + 1]
     Best *partial;            // [kArgmaxBlocks]
     uint32_t *tickets;        // [max_merges + 1] tile tickets, zero-initialised
-    unsigned long long *tile_status;  // [max tiles]
+    unsigned long long *tile_status;  // [max tiles] decoupled look-back (merge_kernel)
     Boundary *boundary;       // this rank's boundary info (device)
     unsigned long long *n_hist;  // [max_merges + 2] stream length before each step
     int rank, world;
@@ -132,14 +132,15 @@ __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long
 // Block-private patch table: the histogram patches of one merge pass are first folded in
 // shared memory (early merge steps hit a few hundred keys millions of times) and flushed
 // to the global table once per CTA per step.
-constexpr int kPatchSlots = 2048;
+constexpr int kPatchBits = 11;
+constexpr int kPatchSlots = 1 << kPatchBits;
 struct PatchTable {
     uint32_t keys[kPatchSlots];
     int vals[kPatchSlots];
 };
 
 __device__ __forceinline__ void patch_add(PatchTable &p, const PairTable &t, uint32_t key, int delta) {
-    uint32_t slot = hash_key(key) & (kPatchSlots - 1);
+    uint32_t slot = (key * 0x9E3779B1u) >> (32 - kPatchBits);  // multiplicative hash: the table is private
 #pragma unroll 1
     for (int probes = 0; probes < 16; probes++) {
         uint32_t k = p.keys[slot];
@@ -370,13 +371,14 @@ __device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, 
 struct MergeSmem {
     Halo halo;
     long long tile;
-    long long scan[kTPB / 32];
+    int scan[kTPB / 32];
     long long lastnon[kTPB / 32];
     unsigned long long prefix;
     long long tile_lastnon;
-    // in[2 + q] = token at tile position q; in[0..1] / in[2 + kTile ..] = 2 / 3 tokens of context
+    // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
-    __align__(16) uint16_t out[kTile];
+    // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
+    __align__(16) uint32_t out[kTile / 2 + 32];
     PatchTable patch;
 };
 
@@ -385,6 +387,13 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+
+// Staging swizzle.  A thread writes ~16 consecutive tokens, so the lanes of a warp start
+// 8 words apart and would pile onto 4 banks; XOR-ing the low 3 bits of the word index with
+// the low 3 bits of its 32-word row spreads them over all 32 banks, and a warp reading 32
+// consecutive words still touches every bank at most twice.
+__device__ __forceinline__ uint32_t stage_word(uint32_t w) { return w ^ ((w >> 5) & 7u); }
+__device__ __forceinline__ uint32_t stage_index(uint32_t x) { return x ^ ((x >> 5) & 14u); }  // 16-bit index
 
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
 // TICKETS: tiles are handed out by an atomic counter (any grid size); otherwise tile =
@@ -398,6 +407,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     const long long n = (long long)v.dev->n[step & 1];
     const long long ntiles = n == 0 ? 1 : (n + kTile - 1) / kTile;
     const bool same = a == b;
+    const uint32_t ab = a | (b << 16);  // a site, as the 32-bit word of two adjacent tokens
 
     __syncthreads();
     if (threadIdx.x == 0) sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
@@ -405,6 +415,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     __syncthreads();
     const Halo h = sm.halo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *const stage16 = reinterpret_cast<uint16_t *>(sm.out);
 
     // token at shard-local position p, including halo context
     auto tok_at = [&](long long p) -> uint32_t {
@@ -428,43 +439,46 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         if (tile >= ntiles) break;
         const long long tbase = tile * kTile;
         const long long base = tbase + (long long)threadIdx.x * kIPT;
+        const int tile_valid = (int)min((long long)kTile, n - tbase);               // tokens of the stream in this tile
+        const int nvalid = min(kIPT, max(0, tile_valid - (int)threadIdx.x * kIPT));  // ... in this thread's range
+        const uint32_t validmask = (1u << nvalid) - 1u;
 
-        // ---- load 16 tokens per thread into registers and into the shared tile ----
-        uint32_t e[kIPT + 2];  // e[1 + i] = token base + i ; e[0] / e[17] = neighbours
-        if (base + kIPT <= n) {
+        // ---- 16 tokens per thread, two per 32-bit word (token 2j = low half of w[j]) ----
+        uint32_t w[kIPT / 2];
+        if (nvalid == kIPT) {
             const uint4 v0 = *reinterpret_cast<const uint4 *>(in + base);
             const uint4 v1 = *reinterpret_cast<const uint4 *>(in + base + 8);
-            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) { e[1 + 2 * i] = w[i] & 0xFFFFu; e[2 + 2 * i] = w[i] >> 16; }
+            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+            w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
         } else {  // end of the shard: positions >= n show the right halo (or the sentinel)
 #pragma unroll
-            for (int i = 0; i < kIPT; i++) e[1 + i] = tok_at(base + i);
+            for (int j = 0; j < kIPT / 2; j++) w[j] = tok_at(base + 2 * j) | (tok_at(base + 2 * j + 1) << 16);
         }
         {
-            uint32_t w[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = e[1 + 2 * i] | (e[2 + 2 * i] << 16);
-            // in[2 + q]: 4-byte aligned rows -> eight 32-bit stores
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.in[2 + threadIdx.x * kIPT]);
-#pragma unroll
-            for (int i = 0; i < 8; i++) dst[i] = w[i];
+            uint4 *dst = reinterpret_cast<uint4 *>(&sm.in[8 + threadIdx.x * kIPT]);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        if (threadIdx.x < 2) sm.in[threadIdx.x] = (uint16_t)tok_at(tbase - 2 + threadIdx.x);
-        if (threadIdx.x >= 2 && threadIdx.x < 5) sm.in[2 + kTile + threadIdx.x - 2] = (uint16_t)tok_at(tbase + kTile + threadIdx.x - 2);
+        if (threadIdx.x < 2) sm.in[6 + threadIdx.x] = (uint16_t)tok_at(tbase - 2 + threadIdx.x);
+        if (threadIdx.x >= 2 && threadIdx.x < 5) sm.in[8 + kTile + threadIdx.x - 2] = (uint16_t)tok_at(tbase + kTile + threadIdx.x - 2);
         __syncthreads();
-        e[0] = sm.in[2 + threadIdx.x * kIPT - 1];
-        e[kIPT + 1] = sm.in[2 + threadIdx.x * kIPT + kIPT];
+        // neighbours of the range: from the adjacent lanes, across warps from the shared tile
+        uint32_t tprev = __shfl_up_sync(0xffffffffu, w[7] >> 16, 1);
+        uint32_t tnext = __shfl_down_sync(0xffffffffu, w[0] & 0xFFFFu, 1);
+        if (lane == 0) tprev = sm.in[8 + threadIdx.x * kIPT - 1];
+        if (lane == 31) tnext = sm.in[8 + threadIdx.x * kIPT + kIPT];
 
-        // ---- (x,x): run offset parity needs the position of the last non-x before each token ----
-        long long run_start = 0;  // start of the x-run that is open when this thread's range begins
+        uint32_t site = 0, removed = 0;  // bit i = position base + i
         if (same) {
-            long long lastnon = -1;
-            bool any = false;
+            // ---- (x,x): run offset parity needs the position of the last non-x before each token ----
+            uint32_t isa = 0;  // bit i: token i is x
 #pragma unroll
-            for (int i = 0; i < kIPT; i++)
-                if (base + i < n && e[1 + i] != a) { lastnon = base + i; any = true; }
-            long long x = any ? lastnon : -(1ll << 62);
+            for (int j = 0; j < kIPT / 2; j++) {
+                if ((w[j] & 0xFFFFu) == a) isa |= 1u << (2 * j);
+                if ((w[j] >> 16) == a) isa |= 2u << (2 * j);
+            }
+            const uint32_t non = ~isa & validmask;
+            long long x = non ? base + (31 - __clz(non)) : -(1ll << 62);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {  // inclusive max-scan inside the warp
                 const long long y = __shfl_up_sync(0xffffffffu, x, o);
@@ -476,8 +490,8 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 bool hit = false;
                 for (long long p = tbase - 1; p >= 0 && !hit; p -= 32) {
                     const long long q = p - lane;
-                    const bool non = q >= 0 && in[q] != a;
-                    const unsigned m = __ballot_sync(0xffffffffu, non);
+                    const bool nonx = q >= 0 && in[q] != a;
+                    const unsigned m = __ballot_sync(0xffffffffu, nonx);
                     if (m) { found = p - (__ffs(m) - 1); hit = true; }
                 }
                 // reached the shard start inside the run: continue it virtually by par_in elements
@@ -486,43 +500,44 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             }
             __syncthreads();
             long long before = sm.tile_lastnon;
-            for (int w = 0; w < warp; w++) before = max(before, sm.lastnon[w]);
+            for (int q = 0; q < warp; q++) before = max(before, sm.lastnon[q]);
             const long long xe = __shfl_up_sync(0xffffffffu, x, 1);
             if (lane > 0) before = max(before, xe);
-            run_start = before + 1;
-        }
-
-        // ---- sites and removed flags ----
-        uint32_t site = 0, removed = 0;  // bit i = position base + i
-        {
-            long long rs = run_start;
+            // odd = parity of the offset inside the run of x that position i belongs to
+            uint32_t odd = (uint32_t)(base - (before + 1)) & 1u;
+            const uint32_t isa_next = (isa >> 1) | ((tnext == a ? 1u : 0u) << (kIPT - 1));
 #pragma unroll
             for (int i = 0; i < kIPT; i++) {
-                const long long p = base + i;
-                const bool valid = p < n;
-                bool st, rm;
-                if (same) {
-                    const bool isa = e[1 + i] == a;
-                    const bool odd = ((p - rs) & 1) != 0;
-                    st = valid && isa && !odd && e[2 + i] == a;
-                    rm = valid && isa && odd;
-                    if (!isa) rs = p + 1;
+                const uint32_t bit = 1u << i;
+                if (isa & bit) {
+                    if (odd) removed |= bit; else if (isa_next & bit) site |= bit;
+                    odd ^= 1u;
                 } else {
-                    st = valid && e[1 + i] == a && e[2 + i] == b;
-                    rm = valid && e[i] == a && e[1 + i] == b;
+                    odd = 0;
                 }
-                site |= (st ? 1u : 0u) << i;
-                removed |= (rm ? 1u : 0u) << i;
             }
+            site &= validmask;
+            removed &= validmask;
+        } else {
+            // ---- a != b: a site is the 32-bit word (a | b << 16) at an even or an odd token offset ----
+#pragma unroll
+            for (int j = 0; j < kIPT / 2; j++) {
+                if (w[j] == ab) site |= 1u << (2 * j);
+                const uint32_t hi = j + 1 < kIPT / 2 ? w[(j + 1) & 7] : tnext;
+                if (__funnelshift_r(w[j], hi, 16) == ab) site |= 2u << (2 * j);
+            }
+            site &= validmask;
+            const uint32_t before = (tprev | (w[0] << 16)) == ab ? 1u : 0u;  // a site at base - 1
+            removed = ((site << 1) | before) & validmask;
         }
 
         // ---- histogram patches, one site at a time (see oracle/ecgb_oracle.c ecgo_train_fast) ----
-        {
+        if (__any_sync(0xffffffffu, site != 0)) {
             int ns = __popc(site);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-            if (lane == 0 && ns) patch_add(sm.patch, upd, mk(a, b), -ns);  // the pair itself, per warp
-            const uint16_t *ctx = &sm.in[threadIdx.x * kIPT];  // ctx[2 + i] = token at base + i
+            if (lane == 0) patch_add(sm.patch, upd, mk(a, b), -ns);  // the pair itself, per warp
+            const uint16_t *ctx = &sm.in[6 + threadIdx.x * kIPT];  // ctx[2 + i] = token at base + i
             uint32_t rem = site;
             while (rem) {
                 const int i = __ffs(rem) - 1;
@@ -541,8 +556,6 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         }
 
         // ---- compaction: kept tokens -> shared staging -> coalesced stores ----
-        uint32_t nvalid = (base >= n) ? 0u : (uint32_t)min((long long)kIPT, n - base);
-        const uint32_t validmask = (1u << nvalid) - 1u;
         const uint32_t keepmask = validmask & ~removed;
         const int kept = __popc(keepmask);
         int incl = kept;
@@ -555,15 +568,23 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         __syncthreads();
         int warp_off = 0, tile_total = 0;
 #pragma unroll
-        for (int w = 0; w < kTPB / 32; w++) {
-            const int c = (int)sm.scan[w];
-            if (w < warp) warp_off += c;
+        for (int q = 0; q < kTPB / 32; q++) {
+            const int c = sm.scan[q];
+            if (q < warp) warp_off += c;
             tile_total += c;
         }
-        int o = warp_off + incl - kept;
+        uint32_t o = (uint32_t)(warp_off + incl - kept);
+        if ((site | removed) == 0 && nvalid == kIPT && (o & 1u) == 0) {
+            // untouched range at an even offset: eight whole words
 #pragma unroll
-        for (int i = 0; i < kIPT; i++)
-            if ((keepmask >> i) & 1u) sm.out[o++] = (uint16_t)(((site >> i) & 1u) ? z : e[1 + i]);
+            for (int j = 0; j < kIPT / 2; j++) sm.out[stage_word((o >> 1) + j)] = w[j];
+        } else {
+#pragma unroll
+            for (int i = 0; i < kIPT; i++) {
+                const uint32_t t = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+                if ((keepmask >> i) & 1u) stage16[stage_index(o++)] = (uint16_t)(((site >> i) & 1u) ? z : t);
+            }
+        }
 
         // decoupled look-back over the tiles that precede this one, 32 tiles per probe (warp 0)
         if (warp == 0) {
@@ -614,7 +635,21 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         }
         __syncthreads();
         const unsigned long long gofs = sm.prefix;
-        for (int k = threadIdx.x; k < tile_total; k += kTPB) out[gofs + k] = sm.out[k];
+        // ---- write-out as 32-bit words; an odd output offset shifts the word boundary by one token ----
+        const int lead = (int)(gofs & 1ull) & (tile_total > 0 ? 1 : 0);
+        const int nwords = (tile_total - lead) >> 1;
+        uint32_t *__restrict__ out32 = reinterpret_cast<uint32_t *>(out + gofs + lead);
+        if (lead) {
+            for (int m = threadIdx.x; m < nwords; m += kTPB) {  // word m = staged tokens 2m+1, 2m+2
+                const uint32_t lo = sm.out[stage_word((uint32_t)m)], hi = sm.out[stage_word((uint32_t)m + 1u)];
+                out32[m] = __funnelshift_r(lo, hi, 16);
+            }
+            if (threadIdx.x == 0) out[gofs] = stage16[0];
+        } else {
+            for (int m = threadIdx.x; m < nwords; m += kTPB) out32[m] = sm.out[stage_word((uint32_t)m)];
+        }
+        if (threadIdx.x == 32 && ((tile_total - lead) & 1))
+            out[gofs + tile_total - 1] = stage16[stage_index((uint32_t)tile_total - 1u)];
     }
     __syncthreads();
     patch_flush(sm.patch, upd);
@@ -647,7 +682,7 @@ __device__ __forceinline__ Best grid_best(cg::grid_group &grid, const TrainView 
     return fin;
 }
 
-__global__ void __launch_bounds__(kTPB) train_loop_kernel(TrainView v, uint32_t n_steps) {
+__global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32_t n_steps) {
     cg::grid_group grid = cg::this_grid();
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
