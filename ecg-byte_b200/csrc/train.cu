@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -44,6 +45,9 @@ constexpr int kIPT = 16;                 // tokens per thread
 constexpr int kTile = kTPB * kIPT;
 constexpr int kBoundaryWords = 16;       // u32 words of boundary info per rank
 constexpr int kArgmaxBlocks = 592;       // 148 SMs x 4
+constexpr uint32_t kRedundantArgmax = 2048;  // candidate lists up to this size are scanned by every CTA
+constexpr int kChunkTiles = 3;           // resident tail: each CTA keeps up to 3 tiles of the stream in shared memory
+constexpr int kChunkCap = kChunkTiles * kTile;
 
 struct PairTable {
     uint32_t *keys;            // left << 16 | right, kEmptyKey = free
@@ -96,6 +100,11 @@ struct TrainView {
     unsigned long long *tile_status;  // [max tiles] decoupled look-back (merge_kernel)
     Boundary *boundary;       // this rank's boundary info (device)
     unsigned long long *n_hist;  // [max_merges + 2] stream length before each step
+    unsigned int *arrive;     // train_loop_kernel: CTAs that have finished the argmax of a step, cumulative
+    Boundary *cta_bd;         // [kArgmaxBlocks] resident tail: boundary record of every CTA's chunk
+    uint32_t *cta_counts;     // [kArgmaxBlocks] resident tail: chunk lengths for the final write-back
+    uint32_t resident_ok;     // resident tail enabled
+    uint32_t redundant_max;   // train_loop_kernel: candidate lists up to this size are scanned by every CTA
     int rank, world;
 };
 
@@ -132,7 +141,7 @@ __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long
 // Block-private patch table: the histogram patches of one merge pass are first folded in
 // shared memory (early merge steps hit a few hundred keys millions of times) and flushed
 // to the global table once per CTA per step.
-constexpr int kPatchBits = 11;
+constexpr int kPatchBits = 10;
 constexpr int kPatchSlots = 1 << kPatchBits;
 struct PatchTable {
     uint32_t keys[kPatchSlots];
@@ -173,6 +182,31 @@ __device__ __forceinline__ void warp_patch_add(PatchTable &p, const PairTable &t
 }
 
 __device__ __forceinline__ uint32_t mk(uint32_t l, uint32_t r) { return (l << 16) | r; }
+
+// Optional phase timing of one CTA of train_loop_kernel (build with ECGB_NVCC_EXTRA=-DECGB_TRAIN_TIMING,
+// run profiles/train_phases.py): thread 0 of CTA 1 accumulates the time between marks.
+#ifdef ECGB_TRAIN_TIMING
+__device__ unsigned long long g_phase[16];
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define ECGB_MARK(i)                                                       \
+    do {                                                                   \
+        if (blockIdx.x == 1 && threadIdx.x == 0) {                         \
+            const unsigned long long t_ = now_ns();                        \
+            g_phase[i] += t_ - t_mark;                                     \
+            t_mark = t_;                                                   \
+        }                                                                  \
+    } while (0)
+#define ECGB_MARK_DECL unsigned long long t_mark = now_ns()
+#define ECGB_MARK_RESET t_mark = now_ns()
+#else
+#define ECGB_MARK(i) do { } while (0)
+#define ECGB_MARK_DECL do { } while (0)
+#define ECGB_MARK_RESET do { } while (0)
+#endif
 
 // ------------------------------------------------------------------ init / count
 
@@ -375,6 +409,8 @@ struct MergeSmem {
     long long lastnon[kTPB / 32];
     unsigned long long prefix;
     long long tile_lastnon;
+    int chunk_n;               // resident tail: tokens of this CTA's chunk
+    uint32_t carry_ctx[2];     // resident tail: last two input tokens of the previous tile
     // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
     // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
@@ -400,19 +436,27 @@ __device__ __forceinline__ uint32_t stage_index(uint32_t x) { return x ^ ((x >> 
 // blockIdx + k * gridDim, which needs every block to be co-resident (cooperative launch).
 template <bool TICKETS>
 __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
-                                           const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm) {
+                                           const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm,
+                                           uint16_t *chunk) {
+    // Resident tail (chunk != nullptr, cooperative kernel only): the stream lives in the CTAs' shared
+    // memory, one contiguous chunk each, and is merged in place; the chunks are shards exactly like the
+    // ranks of a sharded run (all_bd = every CTA's boundary record), so no output offsets are needed.
+    const bool resident = !TICKETS && chunk != nullptr;
     const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
-    const uint16_t *__restrict__ in = v.tok[step & 1];
-    uint16_t *__restrict__ out = v.tok[(step + 1) & 1];
-    const long long n = (long long)v.dev->n[step & 1];
+    const uint16_t *in = resident ? chunk : v.tok[step & 1];
+    uint16_t *out = resident ? chunk : v.tok[(step + 1) & 1];
+    const long long n = resident ? (long long)sm.chunk_n : (long long)v.dev->n[step & 1];
     const long long ntiles = n == 0 ? 1 : (n + kTile - 1) / kTile;
     const bool same = a == b;
     const uint32_t ab = a | (b << 16);  // a site, as the 32-bit word of two adjacent tokens
 
+    ECGB_MARK_DECL;
     __syncthreads();
-    if (threadIdx.x == 0) sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
+    if (threadIdx.x == 0)
+        sm.halo = resident ? make_halo(all_bd, (int)blockIdx.x, (int)gridDim.x, a, b) : make_halo(all_bd, v.rank, v.world, a, b);
     patch_clear(sm.patch);
     __syncthreads();
+    ECGB_MARK(1);
     const Halo h = sm.halo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *const stage16 = reinterpret_cast<uint16_t *>(sm.out);
@@ -425,6 +469,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         return q < (long long)h.nr ? h.R[q] : kSentinel;
     };
 
+    unsigned long long chunk_fill = 0;  // resident: tokens of the chunk written so far
     for (long long round = 0;; round++) {
         long long tile;
         if (TICKETS) {
@@ -433,7 +478,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             __syncthreads();
             tile = sm.tile;
         } else {
-            tile = (long long)blockIdx.x + round * (long long)gridDim.x;
+            tile = resident ? round : (long long)blockIdx.x + round * (long long)gridDim.x;
             __syncthreads();  // shared staging of the previous tile is free again
         }
         if (tile >= ntiles) break;
@@ -459,9 +504,13 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
             dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        if (threadIdx.x < 2) sm.in[6 + threadIdx.x] = (uint16_t)tok_at(tbase - 2 + threadIdx.x);
+        // (resident: the tokens before this tile have already been merged in place; the previous tile left a copy)
+        if (threadIdx.x < 2)
+            sm.in[6 + threadIdx.x] = (uint16_t)((resident && tile > 0) ? sm.carry_ctx[threadIdx.x] : tok_at(tbase - 2 + threadIdx.x));
         if (threadIdx.x >= 2 && threadIdx.x < 5) sm.in[8 + kTile + threadIdx.x - 2] = (uint16_t)tok_at(tbase + kTile + threadIdx.x - 2);
         __syncthreads();
+        ECGB_MARK(2);
+        if (resident && threadIdx.x == kTPB - 1) { sm.carry_ctx[0] = w[7] & 0xFFFFu; sm.carry_ctx[1] = w[7] >> 16; }
         // neighbours of the range: from the adjacent lanes, across warps from the shared tile
         uint32_t tprev = __shfl_up_sync(0xffffffffu, w[7] >> 16, 1);
         uint32_t tnext = __shfl_down_sync(0xffffffffu, w[0] & 0xFFFFu, 1);
@@ -485,7 +534,9 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 if (lane >= o) x = max(x, y);
             }
             if (lane == 31) sm.lastnon[warp] = x;
-            if (warp == 0) {  // run entering the tile: scan backwards from the tile start
+            if (resident) {  // tiles are taken in order: the previous tile left the position in tile_lastnon
+                if (threadIdx.x == 0 && tile == 0) sm.tile_lastnon = -1 - (long long)h.par_in;
+            } else if (warp == 0) {  // run entering the tile: scan backwards from the tile start
                 long long found = -(1ll << 62);
                 bool hit = false;
                 for (long long p = tbase - 1; p >= 0 && !hit; p -= 32) {
@@ -555,6 +606,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             }
         }
 
+        ECGB_MARK(3);
         // ---- compaction: kept tokens -> shared staging -> coalesced stores ----
         const uint32_t keepmask = validmask & ~removed;
         const int kept = __popc(keepmask);
@@ -566,6 +618,12 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         }
         if (lane == 31) sm.scan[warp] = incl;
         __syncthreads();
+        ECGB_MARK(4);
+        if (resident && same && threadIdx.x == 0) {  // every thread has read tile_lastnon: carry it to the next tile
+            long long m = sm.tile_lastnon;
+            for (int q = 0; q < kTPB / 32; q++) m = max(m, sm.lastnon[q]);
+            sm.tile_lastnon = m;
+        }
         int warp_off = 0, tile_total = 0;
 #pragma unroll
         for (int q = 0; q < kTPB / 32; q++) {
@@ -586,8 +644,9 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             }
         }
 
+        ECGB_MARK(5);
         // decoupled look-back over the tiles that precede this one, 32 tiles per probe (warp 0)
-        if (warp == 0) {
+        if (warp == 0 && !resident) {
             unsigned long long excl = 0;
             if (tile > 0) {
                 if (lane == 0) atomicExch(&v.tile_status[tile], pack_status(1, step, (unsigned long long)tile_total));
@@ -633,8 +692,11 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 }
             }
         }
+        ECGB_MARK(6);
         __syncthreads();
-        const unsigned long long gofs = sm.prefix;
+        ECGB_MARK(7);
+        const unsigned long long gofs = resident ? chunk_fill : sm.prefix;  // resident: the chunk is compacted in place
+        chunk_fill += (unsigned long long)tile_total;
         // ---- write-out as 32-bit words; an odd output offset shifts the word boundary by one token ----
         const int lead = (int)(gofs & 1ull) & (tile_total > 0 ? 1 : 0);
         const int nwords = (tile_total - lead) >> 1;
@@ -650,9 +712,52 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         }
         if (threadIdx.x == 32 && ((tile_total - lead) & 1))
             out[gofs + tile_total - 1] = stage16[stage_index((uint32_t)tile_total - 1u)];
+        ECGB_MARK(8);
+    }
+    if (resident && threadIdx.x == 0) {
+        sm.chunk_n = (int)chunk_fill;
+        if (chunk_fill) atomicAdd(&v.n_hist[step + 1], chunk_fill);  // stream length after this step (zero-initialised)
+    }
+    if (!TICKETS) {
+        // the histogram may only change once every CTA has taken this step's argmax from it (CTAs scan
+        // short candidate lists on their own, without a grid barrier): cumulative arrival counter
+        if (threadIdx.x == 0) {
+            const unsigned int target = (step + 1u) * gridDim.x;
+            while (*reinterpret_cast<volatile unsigned int *>(v.arrive) < target) { }
+        }
     }
     __syncthreads();
     patch_flush(sm.patch, upd);
+    ECGB_MARK(9);
+}
+
+// Resident tail: boundary record of this CTA's chunk for the pair (a, b) (the same record a rank
+// publishes for its shard).  Warp 0 only.
+__device__ __forceinline__ void chunk_boundary(const uint16_t *chunk, int n, uint32_t a, bool same, Boundary *dst) {
+    const int lane = threadIdx.x & 31;
+    int run = 0;
+    if (same) {  // length of the trailing run of a
+        int found = -1;
+        bool hit = false;
+        for (int p = n - 1; p >= 0 && !hit; p -= 32) {
+            const int q = p - lane;
+            const bool nonx = q >= 0 && chunk[q] != a;
+            const unsigned m = __ballot_sync(0xffffffffu, nonx);
+            if (m) { found = p - (__ffs(m) - 1); hit = true; }
+        }
+        run = n - 1 - found;
+    }
+    if (lane == 0) {
+        Boundary bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.n_lo = (uint32_t)n;
+        for (int i = 0; i < 3; i++) bd.first[i] = i < n ? (uint32_t)chunk[i] : kSentinel;
+        bd.last[1] = n >= 1 ? (uint32_t)chunk[n - 1] : kSentinel;
+        bd.last[0] = n >= 2 ? (uint32_t)chunk[n - 2] : kSentinel;
+        bd.trail_par = (uint32_t)(run & 1);
+        bd.all_a = same && run == n ? 1u : 0u;
+        *dst = bd;
+    }
 }
 
 __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
@@ -660,7 +765,7 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
     __shared__ MergeSmem sm;
     const Best bb = v.best[step];
     if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
-    merge_pass<true>(v, step, bb, all_bd, upd, sm);
+    merge_pass<true>(v, step, bb, all_bd, upd, sm, nullptr);
 }
 
 // The whole single-device training loop (lib.rs:85-117) as ONE persistent cooperative
@@ -686,19 +791,54 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
     cg::grid_group grid = cg::this_grid();
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
+    extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
+    bool res_mode = false;
     const PairTable &t = v.main;
     const uint64_t cap = (uint64_t)t.mask + 1;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long *tau = const_cast<unsigned long long *>(t.tau);
-    for (uint32_t step = 0; step < n_steps; step++) {
+    ECGB_MARK_DECL;
+    uint32_t step = 0;
+    for (; step < n_steps; step++) {
+        ECGB_MARK_RESET;
+        if (!res_mode && v.resident_ok) {
+            // the stream now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
+            const unsigned long long n = v.dev->n[step & 1];
+            const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;
+            if (clen <= (unsigned long long)kChunkCap) {
+                const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
+                const unsigned long long hi = min(n, lo + clen);
+                const uint16_t *src = v.tok[step & 1] + lo;  // lo is a multiple of 8 tokens: 16-byte aligned
+                const int cn = (int)(hi - lo);
+                for (int i = threadIdx.x * 8; i + 8 <= cn; i += kTPB * 8)
+                    *reinterpret_cast<uint4 *>(chunk + i) = *reinterpret_cast<const uint4 *>(src + i);
+                for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk[i] = src[i];
+                if (threadIdx.x == 0) sm.chunk_n = cn;
+                res_mode = true;
+                __syncthreads();
+            }
+        }
         // ---- argmax (lib.rs:92-94): over the candidate list; every pair whose count is >= tau
         //      is listed, so a listed maximum >= tau is the global one (with all its ties)
         const unsigned long long cur_tau = *tau;
         const uint32_t nc = *t.ncand;
         Best mine{0, kEmptyKey, 0};
         Best fin;
-        if (nc <= 8 * kTPB) {
+        if (nc <= v.redundant_max) {
+            // very short list (the usual case in the long tail): every CTA scans it and reaches the same
+            // winner by itself -- no grid barrier between the histogram and the merge pass
+            for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+                const uint32_t slot = t.cand[i];
+                const unsigned long long c = t.cnt[slot];
+                if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+            }
+            const Best b0 = block_best(mine);
+            __syncthreads();
+            if (threadIdx.x == 0) s_best = b0;
+            __syncthreads();
+            fin = s_best;
+        } else if (nc <= 8 * kTPB) {
             // short list: block 0 scans it alone, one grid barrier publishes the winner
             if (blockIdx.x == 0) {
                 for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
@@ -746,8 +886,41 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
             if (fin.count == 0) atomicMin(&v.dev->done_step, step);
         }
         if (fin.count == 0) break;  // no pair left (lib.rs:88-90); uniform over the grid
-        merge_pass<false>(v, step, fin, nullptr, v.main, sm);
+        if (threadIdx.x == 0) atomicAdd(v.arrive, 1u);  // this CTA no longer reads the histogram in this step
+        ECGB_MARK(0);
+        if (res_mode) {
+            if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, (fin.key >> 16) == (fin.key & 0xFFFFu), &v.cta_bd[blockIdx.x]);
+            grid.sync();  // every chunk's boundary record is visible
+        }
+        merge_pass<false>(v, step, fin, res_mode ? v.cta_bd : nullptr, v.main, sm, res_mode ? chunk : nullptr);
+        ECGB_MARK_RESET;
         grid.sync();
+        ECGB_MARK(10);
+    }
+    if (res_mode) {
+        // back to one contiguous stream in tok[step & 1] (step = merges done), where the host expects it
+        const int cn = sm.chunk_n;
+        if (threadIdx.x == 0) v.cta_counts[blockIdx.x] = (uint32_t)cn;
+        grid.sync();
+        unsigned long long pre = 0, all = 0;
+        for (uint32_t j = threadIdx.x; j < gridDim.x; j += kTPB) {
+            const unsigned long long c = __ldcg(&v.cta_counts[j]);
+            all += c;
+            if (j < blockIdx.x) pre += c;
+        }
+        __shared__ unsigned long long s_pre[kTPB / 32], s_all[kTPB / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pre += __shfl_xor_sync(0xffffffffu, pre, o);
+            all += __shfl_xor_sync(0xffffffffu, all, o);
+        }
+        if ((threadIdx.x & 31) == 0) { s_pre[threadIdx.x >> 5] = pre; s_all[threadIdx.x >> 5] = all; }
+        __syncthreads();
+        pre = all = 0;
+        for (int q = 0; q < kTPB / 32; q++) { pre += s_pre[q]; all += s_all[q]; }
+        uint16_t *dst = v.tok[step & 1] + pre;
+        for (int i = threadIdx.x; i < cn; i += kTPB) dst[i] = chunk[i];
+        if (blockIdx.x == 0 && threadIdx.x == 0) v.dev->n[step & 1] = all;
     }
 }
 
@@ -875,6 +1048,9 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tile_status, 8 * ntiles, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.n_hist, 8 * ((size_t)max_merges + 2), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.arrive, 16, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_bd, sizeof(Boundary) * kArgmaxBlocks, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_counts, 4 * kArgmaxBlocks, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->d_list, (size_t)(4 + 3 * (size_t)t->list_cap) * 4, true);
     if (rc) { ecgb_trainer_destroy(t); return rc; }
     t->v.rank = 0;
@@ -912,6 +1088,7 @@ static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
     ECGB_CUDA(cudaMemsetAsync(t->v.delta.used, 0, 8, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.tickets, 0, 4 * ((size_t)t->max_merges + 1), st));
     ECGB_CUDA(cudaMemsetAsync(t->v.n_hist, 0, 8 * ((size_t)t->max_merges + 2), st));
+    ECGB_CUDA(cudaMemsetAsync(t->v.arrive, 0, 16, st));
     ECGB_CUDA(cudaMemcpyAsync(t->v.n_hist, &t->v.dev->n[0], 8, cudaMemcpyDeviceToDevice, st));
     ECGB_CUDA(cudaMemsetAsync(t->v.best, 0, sizeof(Best) * ((size_t)t->max_merges + 1), st));
     ECGB_CUDA(cudaMemsetAsync(t->v.tile_status, 0, 8 * ((size_t)(t->capacity / kTile) + 2), st));
@@ -980,18 +1157,34 @@ extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *
     ECGB_CUDA(cudaGetLastError());
     // one persistent cooperative kernel runs every step (grid = all co-resident CTAs)
     int per_sm = 0;
-    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_loop_kernel, kTPB, 0));
+    const size_t dyn_smem = (size_t)kChunkCap * sizeof(uint16_t);
+    ECGB_CUDA(cudaFuncSetAttribute(train_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_loop_kernel, kTPB, dyn_smem));
     if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "train_loop_kernel does not fit on this device");
     int grid = t->sms * std::min(per_sm, 4);
     if (grid > kArgmaxBlocks) grid = kArgmaxBlocks;
     if (num_merges > 0) {
         TrainView view = t->v;
+        const char *knob = getenv("ECGB_REDUNDANT_ARGMAX");  // tuning knob (profiles/train_knobs.py)
+        view.redundant_max = knob ? (uint32_t)atoi(knob) : kRedundantArgmax;
+        knob = getenv("ECGB_RESIDENT_TAIL");
+        view.resident_ok = knob ? (uint32_t)atoi(knob) : 1u;
         uint32_t steps = num_merges;
         void *kargs[] = {&view, &steps};
-        ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)train_loop_kernel, dim3(grid), dim3(kTPB), kargs, 0, st));
+        ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)train_loop_kernel, dim3(grid), dim3(kTPB), kargs, dyn_smem, st));
     }
     ECGB_CUDA(cudaGetLastError());
     ECGB_CUDA(cudaStreamSynchronize(st));
+#ifdef ECGB_TRAIN_TIMING
+    {
+        unsigned long long ph[16], zero[16] = {0};
+        cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph));
+        cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
+        static const char *names[11] = {"argmax", "pass setup", "tile load+sync", "flags+patches", "scan+sync", "stage",
+                                        "look-back", "sync", "write-out", "patch flush", "grid sync"};
+        for (int i = 0; i < 11; i++) fprintf(stderr, "phase %-14s %10.3f ms\n", names[i], ph[i] * 1e-6);
+    }
+#endif
     int rc = check_tables(t);
     if (rc) return rc;
     DevState hs;
