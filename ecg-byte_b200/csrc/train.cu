@@ -101,7 +101,7 @@ struct TrainView {
     Boundary *boundary;       // this rank's boundary info (device)
     unsigned long long *n_hist;  // [max_merges + 2] stream length before each step
     unsigned int *arrive;     // train_loop_kernel: CTAs that have finished the argmax of a step, cumulative
-    Boundary *cta_bd;         // [kArgmaxBlocks] resident tail: boundary record of every CTA's chunk
+    Boundary *cta_bd;         // [2][kArgmaxBlocks] resident tail: boundary record of every CTA's chunk, by step parity
     uint32_t *cta_counts;     // [kArgmaxBlocks] resident tail: chunk lengths for the final write-back
     uint32_t resident_ok;     // resident tail enabled
     uint32_t redundant_max;   // train_loop_kernel: candidate lists up to this size are scanned by every CTA
@@ -424,6 +424,35 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
     return v;
 }
 
+// Resident tail: boundary record of this CTA's chunk for the pair (a, b) (the same record a rank
+// publishes for its shard).  Warp 0 only.
+__device__ __forceinline__ void chunk_boundary(const uint16_t *chunk, int n, uint32_t a, bool same, Boundary *dst) {
+    const int lane = threadIdx.x & 31;
+    int run = 0;
+    if (same) {  // length of the trailing run of a
+        int found = -1;
+        bool hit = false;
+        for (int p = n - 1; p >= 0 && !hit; p -= 32) {
+            const int q = p - lane;
+            const bool nonx = q >= 0 && chunk[q] != a;
+            const unsigned m = __ballot_sync(0xffffffffu, nonx);
+            if (m) { found = p - (__ffs(m) - 1); hit = true; }
+        }
+        run = n - 1 - found;
+    }
+    if (lane == 0) {
+        Boundary bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.n_lo = (uint32_t)n;
+        for (int i = 0; i < 3; i++) bd.first[i] = i < n ? (uint32_t)chunk[i] : kSentinel;
+        bd.last[1] = n >= 1 ? (uint32_t)chunk[n - 1] : kSentinel;
+        bd.last[0] = n >= 2 ? (uint32_t)chunk[n - 2] : kSentinel;
+        bd.trail_par = (uint32_t)(run & 1);
+        bd.all_a = same && run == n ? 1u : 0u;
+        *dst = bd;
+    }
+}
+
 // Staging swizzle.  A thread writes ~16 consecutive tokens, so the lanes of a warp start
 // 8 words apart and would pile onto 4 banks; XOR-ing the low 3 bits of the word index with
 // the low 3 bits of its 32-word row spreads them over all 32 banks, and a warp reading 32
@@ -434,17 +463,18 @@ __device__ __forceinline__ uint32_t stage_index(uint32_t x) { return x ^ ((x >> 
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
 // TICKETS: tiles are handed out by an atomic counter (any grid size); otherwise tile =
 // blockIdx + k * gridDim, which needs every block to be co-resident (cooperative launch).
-template <bool TICKETS>
+template <bool TICKETS, bool RESIDENT>
 __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
                                            const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm,
                                            uint16_t *chunk) {
     // Resident tail (chunk != nullptr, cooperative kernel only): the stream lives in the CTAs' shared
     // memory, one contiguous chunk each, and is merged in place; the chunks are shards exactly like the
     // ranks of a sharded run (all_bd = every CTA's boundary record), so no output offsets are needed.
-    const bool resident = !TICKETS && chunk != nullptr;
+    static_assert(!(TICKETS && RESIDENT), "the resident tail belongs to the cooperative kernel");
+    constexpr bool resident = RESIDENT;
     const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
-    const uint16_t *in = resident ? chunk : v.tok[step & 1];
-    uint16_t *out = resident ? chunk : v.tok[(step + 1) & 1];
+    const uint16_t *__restrict__ in = resident ? chunk : v.tok[step & 1];
+    uint16_t *__restrict__ out = resident ? chunk : v.tok[(step + 1) & 1];
     const long long n = resident ? (long long)sm.chunk_n : (long long)v.dev->n[step & 1];
     const long long ntiles = n == 0 ? 1 : (n + kTile - 1) / kTile;
     const bool same = a == b;
@@ -714,9 +744,15 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             out[gofs + tile_total - 1] = stage16[stage_index((uint32_t)tile_total - 1u)];
         ECGB_MARK(8);
     }
-    if (resident && threadIdx.x == 0) {
-        sm.chunk_n = (int)chunk_fill;
-        if (chunk_fill) atomicAdd(&v.n_hist[step + 1], chunk_fill);  // stream length after this step (zero-initialised)
+    if (resident) {
+        __syncthreads();  // the chunk is complete
+        // record for the next step (other parity: slower CTAs may still be reading this step's records);
+        // an (x,x) step adds the run information and a grid barrier of its own
+        if (warp == 0) chunk_boundary(chunk, (int)chunk_fill, kSentinel, false, &v.cta_bd[((step + 1) & 1) * kArgmaxBlocks + blockIdx.x]);
+        if (threadIdx.x == 0) {
+            sm.chunk_n = (int)chunk_fill;
+            if (chunk_fill) atomicAdd(&v.n_hist[step + 1], chunk_fill);  // stream length after this step (zero-initialised)
+        }
     }
     if (!TICKETS) {
         // the histogram may only change once every CTA has taken this step's argmax from it (CTAs scan
@@ -731,41 +767,12 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     ECGB_MARK(9);
 }
 
-// Resident tail: boundary record of this CTA's chunk for the pair (a, b) (the same record a rank
-// publishes for its shard).  Warp 0 only.
-__device__ __forceinline__ void chunk_boundary(const uint16_t *chunk, int n, uint32_t a, bool same, Boundary *dst) {
-    const int lane = threadIdx.x & 31;
-    int run = 0;
-    if (same) {  // length of the trailing run of a
-        int found = -1;
-        bool hit = false;
-        for (int p = n - 1; p >= 0 && !hit; p -= 32) {
-            const int q = p - lane;
-            const bool nonx = q >= 0 && chunk[q] != a;
-            const unsigned m = __ballot_sync(0xffffffffu, nonx);
-            if (m) { found = p - (__ffs(m) - 1); hit = true; }
-        }
-        run = n - 1 - found;
-    }
-    if (lane == 0) {
-        Boundary bd;
-        memset(&bd, 0, sizeof(bd));
-        bd.n_lo = (uint32_t)n;
-        for (int i = 0; i < 3; i++) bd.first[i] = i < n ? (uint32_t)chunk[i] : kSentinel;
-        bd.last[1] = n >= 1 ? (uint32_t)chunk[n - 1] : kSentinel;
-        bd.last[0] = n >= 2 ? (uint32_t)chunk[n - 2] : kSentinel;
-        bd.trail_par = (uint32_t)(run & 1);
-        bd.all_a = same && run == n ? 1u : 0u;
-        *dst = bd;
-    }
-}
-
 __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
                                                      PairTable upd) {
     __shared__ MergeSmem sm;
     const Best bb = v.best[step];
     if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
-    merge_pass<true>(v, step, bb, all_bd, upd, sm, nullptr);
+    merge_pass<true, false>(v, step, bb, all_bd, upd, sm, nullptr);
 }
 
 // The whole single-device training loop (lib.rs:85-117) as ONE persistent cooperative
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
     extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
-    bool res_mode = false;
+    bool res_mode = false, res_fresh = false;
     const PairTable &t = v.main;
     const uint64_t cap = (uint64_t)t.mask + 1;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -815,7 +822,7 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
                     *reinterpret_cast<uint4 *>(chunk + i) = *reinterpret_cast<const uint4 *>(src + i);
                 for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk[i] = src[i];
                 if (threadIdx.x == 0) sm.chunk_n = cn;
-                res_mode = true;
+                res_mode = res_fresh = true;
                 __syncthreads();
             }
         }
@@ -889,10 +896,15 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
         if (threadIdx.x == 0) atomicAdd(v.arrive, 1u);  // this CTA no longer reads the histogram in this step
         ECGB_MARK(0);
         if (res_mode) {
-            if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, (fin.key >> 16) == (fin.key & 0xFFFFu), &v.cta_bd[blockIdx.x]);
-            grid.sync();  // every chunk's boundary record is visible
+            const bool xx = (fin.key >> 16) == (fin.key & 0xFFFFu);
+            if (xx || res_fresh) {  // otherwise the records published by the previous pass are all that is needed
+                if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, xx, &v.cta_bd[(step & 1) * kArgmaxBlocks + blockIdx.x]);
+                grid.sync();  // every chunk's boundary record is visible
+            }
+            res_fresh = false;
         }
-        merge_pass<false>(v, step, fin, res_mode ? v.cta_bd : nullptr, v.main, sm, res_mode ? chunk : nullptr);
+        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (step & 1) * kArgmaxBlocks, v.main, sm, chunk);
+        else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr);
         ECGB_MARK_RESET;
         grid.sync();
         ECGB_MARK(10);
@@ -1049,7 +1061,7 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
     if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.n_hist, 8 * ((size_t)max_merges + 2), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.arrive, 16, true);
-    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_bd, sizeof(Boundary) * kArgmaxBlocks, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_bd, sizeof(Boundary) * 2 * kArgmaxBlocks, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_counts, 4 * kArgmaxBlocks, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->d_list, (size_t)(4 + 3 * (size_t)t->list_cap) * 4, true);
     if (rc) { ecgb_trainer_destroy(t); return rc; }
