@@ -117,7 +117,9 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t k) {
     return k;
 }
 
-__device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta) {
+// tau_val: the candidate threshold (*t.tau), read by the caller once -- it only changes between passes,
+// and loading it here would put one more L2 round trip behind every atomic
+__device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta, unsigned long long tau_val) {
     uint32_t slot = hash_key(key) & t.mask;
     for (uint32_t probes = 0; probes <= t.mask; probes++) {
         uint32_t k = t.keys[slot];
@@ -127,7 +129,7 @@ __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long
         }
         if (k == key) {
             const unsigned long long old = atomicAdd(&t.cnt[slot], (unsigned long long)delta);
-            if (delta > 0 && t.tau != nullptr && old + (unsigned long long)delta >= *t.tau) {
+            if (delta > 0 && t.tau != nullptr && old + (unsigned long long)delta >= tau_val) {
                 const uint32_t bit = 1u << (slot & 31);
                 if (!(atomicOr(&t.inbits[slot >> 5], bit) & bit)) t.cand[atomicAdd(t.ncand, 1u)] = slot;
             }
@@ -147,6 +149,10 @@ struct PatchTable {
     uint32_t keys[kPatchSlots];
     int vals[kPatchSlots];
 };
+
+__device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta) {
+    table_add(t, key, delta, t.tau != nullptr ? *t.tau : ~0ull);
+}
 
 __device__ __forceinline__ void patch_add(PatchTable &p, const PairTable &t, uint32_t key, int delta) {
     uint32_t slot = (key * 0x9E3779B1u) >> (32 - kPatchBits);  // multiplicative hash: the table is private
@@ -170,9 +176,9 @@ __device__ __forceinline__ void patch_clear(PatchTable &p) {
     for (int i = threadIdx.x; i < kPatchSlots; i += blockDim.x) { p.keys[i] = kEmptyKey; p.vals[i] = 0; }
 }
 
-__device__ __forceinline__ void patch_flush(PatchTable &p, const PairTable &t) {
+__device__ __forceinline__ void patch_flush(PatchTable &p, const PairTable &t, unsigned long long tau_val) {
     for (int i = threadIdx.x; i < kPatchSlots; i += blockDim.x)
-        if (p.keys[i] != kEmptyKey && p.vals[i] != 0) table_add(t, p.keys[i], (long long)p.vals[i]);
+        if (p.keys[i] != kEmptyKey && p.vals[i] != 0) table_add(t, p.keys[i], (long long)p.vals[i], tau_val);
 }
 
 // All 32 lanes call; lanes with the same key are folded into one atomic.
@@ -363,20 +369,22 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t flag, uint32_
     return ((unsigned long long)flag << 62) | ((unsigned long long)((step + 1) & 0xFFFFF) << 42) | (count & kCountMask);
 }
 
-__device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, uint32_t b) {
+// rec(r) = boundary record of shard r
+template <class Rec>
+__device__ __forceinline__ Halo make_halo_from(Rec rec, bool have, int rank, int world, uint32_t a, uint32_t b) {
     Halo h;
     h.nl = h.nr = 0;
     h.L[0] = h.L[1] = kSentinel;
     h.R[0] = h.R[1] = h.R[2] = kSentinel;
     h.par_in = 0;
-    if (world <= 1 || all == nullptr) return h;
+    if (world <= 1 || !have) return h;
     // left context: the last two tokens of the stream before this shard
     uint32_t got[2];
     int ng = 0;
     for (int r = rank - 1; r >= 0 && ng < 2; r--) {
-        const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
-        if (n >= 1) got[ng++] = all[r].last[1];
-        if (n >= 2 && ng < 2) got[ng++] = all[r].last[0];
+        const unsigned long long n = ((unsigned long long)rec(r).n_hi << 32) | rec(r).n_lo;
+        if (n >= 1) got[ng++] = rec(r).last[1];
+        if (n >= 2 && ng < 2) got[ng++] = rec(r).last[0];
     }
     h.nl = ng;
     if (ng >= 1) h.L[1] = got[0];
@@ -384,22 +392,26 @@ __device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, 
     // right context: the first three tokens of the stream after this shard
     int nr = 0;
     for (int r = rank + 1; r < world && nr < 3; r++) {
-        const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
-        for (int i = 0; i < 3 && (unsigned long long)i < n && nr < 3; i++) h.R[nr++] = all[r].first[i];
+        const unsigned long long n = ((unsigned long long)rec(r).n_hi << 32) | rec(r).n_lo;
+        for (int i = 0; i < 3 && (unsigned long long)i < n && nr < 3; i++) h.R[nr++] = rec(r).first[i];
     }
     h.nr = nr;
     if (a == b) {
         uint32_t par = 0;
         for (int r = rank - 1; r >= 0; r--) {
-            const unsigned long long n = ((unsigned long long)all[r].n_hi << 32) | all[r].n_lo;
+            const unsigned long long n = ((unsigned long long)rec(r).n_hi << 32) | rec(r).n_lo;
             if (n == 0) continue;
-            if (all[r].all_a) { par ^= (uint32_t)(n & 1); continue; }
-            par ^= all[r].trail_par;
+            if (rec(r).all_a) { par ^= (uint32_t)(n & 1); continue; }
+            par ^= rec(r).trail_par;
             break;
         }
         h.par_in = par;
     }
     return h;
+}
+
+__device__ Halo make_halo(const Boundary *all, int rank, int world, uint32_t a, uint32_t b) {
+    return make_halo_from([&](int r) -> const Boundary & { return all[r]; }, all != nullptr, rank, world, a, b);
 }
 
 struct MergeSmem {
@@ -409,8 +421,10 @@ struct MergeSmem {
     long long lastnon[kTPB / 32];
     unsigned long long prefix;
     long long tile_lastnon;
+    unsigned long long tau_val;  // candidate threshold of the table the patches go to, read once per pass
     int chunk_n;               // resident tail: tokens of this CTA's chunk
     uint32_t carry_ctx[2];     // resident tail: last two input tokens of the previous tile
+    Boundary bd_near[5];       // resident tail: records of chunks blockIdx-2 .. blockIdx+2
     // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
     // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
@@ -482,8 +496,24 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
 
     ECGB_MARK_DECL;
     __syncthreads();
-    if (threadIdx.x == 0)
-        sm.halo = resident ? make_halo(all_bd, (int)blockIdx.x, (int)gridDim.x, a, b) : make_halo(all_bd, v.rank, v.world, a, b);
+    if (threadIdx.x == 32) sm.tau_val = upd.tau != nullptr ? *upd.tau : ~0ull;
+    if (resident) {
+        // the neighbours' records in one round trip; make_halo rarely needs anything further away
+        const int me = (int)blockIdx.x;
+        if (threadIdx.x >= 64 && threadIdx.x < 64 + 5 * kBoundaryWords) {
+            const int q = (threadIdx.x - 64) / kBoundaryWords, wd = (threadIdx.x - 64) % kBoundaryWords;
+            const int r = me - 2 + q;
+            if (r >= 0 && r < (int)gridDim.x)
+                reinterpret_cast<uint32_t *>(&sm.bd_near[q])[wd] = reinterpret_cast<const uint32_t *>(&all_bd[r])[wd];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            sm.halo = make_halo_from(
+                [&](int r) -> const Boundary & { return (r >= me - 2 && r <= me + 2) ? sm.bd_near[r - me + 2] : all_bd[r]; },
+                true, me, (int)gridDim.x, a, b);
+    } else if (threadIdx.x == 0) {
+        sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
+    }
     patch_clear(sm.patch);
     __syncthreads();
     ECGB_MARK(1);
@@ -763,7 +793,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         }
     }
     __syncthreads();
-    patch_flush(sm.patch, upd);
+    patch_flush(sm.patch, upd, sm.tau_val);
     ECGB_MARK(9);
 }
 
