@@ -3,23 +3,28 @@
 //   reverse_normalize_all  ecg_byte/utils/tokenizer_utils.py:22-28     -> ecgb_dequantize
 //   ECGTokenDataset: signal_k -> LLM id (data_loader.py:80), truncate / left-pad / labels /
 //   attention mask / position ids (data_loader.py:26-31, 101-132)      -> ecgb_pack_training
+//   expand_attention       ecg_byte/runners/interpret.py:106-111       -> ecgb_expand_attention
+//   analyze_token_distribution (Counter over encoded ids) tokenizer_utils.py:30-54 -> ecgb_token_histogram
 #include <algorithm>
 
 #include "common.h"
 
 namespace ecgb {
 
-// One CTA per record: prefix sum of the token lengths, then every token copies its bytes.
+// One CTA per record: prefix sum of the token lengths, then every token copies its bytes
+// (decode_text) or repeats its attention value once per symbol (ATTN: expand_attention).
+template <bool ATTN, class Out>
 __global__ void __launch_bounds__(256) decode_kernel(const int32_t *__restrict__ tokens, size_t in_stride,
-                                                     const int32_t *__restrict__ lens, uint8_t *__restrict__ sym,
+                                                     const int32_t *__restrict__ lens, Out *__restrict__ sym,
                                                      size_t sym_stride, int32_t *__restrict__ sym_len,
                                                      const uint8_t *__restrict__ dec_sym,
-                                                     const uint32_t *__restrict__ dec_off, uint32_t dec_ids, int *bad) {
+                                                     const uint32_t *__restrict__ dec_off, uint32_t dec_ids, int *bad,
+                                                     const float *__restrict__ attn) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_carry;
     const size_t r = blockIdx.x;
     const int32_t *tok = tokens + r * in_stride;
-    uint8_t *out = sym + r * sym_stride;
+    Out *out = sym + r * sym_stride;
     const uint32_t n = (uint32_t)min((long long)max(lens[r], 0), (long long)in_stride);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
@@ -43,8 +48,14 @@ __global__ void __launch_bounds__(256) decode_kernel(const int32_t *__restrict__
         uint32_t woff = 0, total = 0;
         for (int w = 0; w < 8; w++) { if (w < warp) woff += s_warp[w]; total += s_warp[w]; }
         const uint32_t dst = s_carry + woff + incl - l;
-        for (uint32_t k = 0; k < l; k++)
-            if (dst + k < sym_stride) out[dst + k] = dec_sym[o + k];
+        if constexpr (ATTN) {
+            const float av = i < n ? attn[r * in_stride + i] : 0.f;
+            for (uint32_t k = 0; k < l; k++)
+                if (dst + k < sym_stride) out[dst + k] = av;
+        } else {
+            for (uint32_t k = 0; k < l; k++)
+                if (dst + k < sym_stride) out[dst + k] = dec_sym[o + k];
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
@@ -146,6 +157,37 @@ __global__ void __launch_bounds__(256) pack_kernel(const int32_t *__restrict__ t
 
 }  // namespace ecgb
 
+namespace ecgb {
+// Counter over the encoded ids of a batch (tokenizer_utils.py:44-49): block-private counts in shared
+// memory while the id space fits, one 64-bit atomic per (CTA, id) at the end.
+constexpr uint32_t kHistSmemIds = 11264;  // 44 KB of u32 counters
+template <bool PRIV>
+__global__ void __launch_bounds__(256) token_hist_kernel(const int32_t *__restrict__ tokens, size_t in_stride,
+                                                         const int32_t *__restrict__ lens, size_t n_rec, uint32_t n_ids,
+                                                         unsigned long long *__restrict__ counts, int *bad) {
+    __shared__ uint32_t s_cnt[PRIV ? kHistSmemIds : 1];
+    if (PRIV) {
+        for (uint32_t i = threadIdx.x; i < n_ids; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+    }
+    for (size_t r = blockIdx.x; r < n_rec; r += gridDim.x) {
+        const int32_t *tok = tokens + r * in_stride;
+        const uint32_t n = (uint32_t)min((long long)max(lens[r], 0), (long long)in_stride);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t t = (uint32_t)tok[i];
+            if (t >= n_ids) { atomicExch(bad, 1); continue; }
+            if (PRIV) atomicAdd(&s_cnt[t], 1u);
+            else atomicAdd(&counts[t], 1ull);
+        }
+    }
+    if (PRIV) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_ids; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+    }
+}
+}  // namespace ecgb
+
 using namespace ecgb;
 
 extern "C" int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens, size_t n_rec, size_t in_stride,
@@ -162,14 +204,63 @@ extern "C" int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens,
     int *d_bad = nullptr;
     ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
     ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-    decode_kernel<<<(unsigned)n_rec, 256, 0, st>>>(d_tokens, in_stride, d_len, d_sym, sym_stride, d_sym_len, vv->d_dec_sym,
-                                                   vv->d_dec_off, vv->dec_ids, d_bad);
+    decode_kernel<false, uint8_t><<<(unsigned)n_rec, 256, 0, st>>>(d_tokens, in_stride, d_len, d_sym, sym_stride, d_sym_len,
+                                                                   vv->d_dec_sym, vv->d_dec_off, vv->dec_ids, d_bad, nullptr);
     ECGB_CUDA(cudaGetLastError());
     int bad = 0;
     ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
     ECGB_CUDA(cudaFreeAsync(d_bad, st));
     if (bad) return fail(ECGB_EINVAL, "a token id is not in the vocabulary (decode_text would raise KeyError)");
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_expand_attention(const ecgb_vocab *v, const int32_t *d_tokens, const float *d_attn, size_t n_rec,
+                                     size_t in_stride, const int32_t *d_len, float *d_out, size_t out_stride,
+                                     int32_t *d_out_len, void *stream) {
+    ECGB_REQUIRE(v, "vocab is NULL");
+    if (n_rec == 0) return ECGB_OK;
+    ECGB_REQUIRE(d_tokens && d_attn && d_len && d_out && d_out_len, "NULL buffer");
+    const VocabView *vv = ecgb_vocab_view(v);
+    ECGB_REQUIRE(vv->d_dec_off != nullptr, "vocabulary has no decode table (token ids too large)");
+    DeviceGuard g(ecgb_vocab_device(v));
+    cudaStream_t st = as_stream(stream);
+    int *d_bad = nullptr;
+    ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
+    ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    decode_kernel<true, float><<<(unsigned)n_rec, 256, 0, st>>>(d_tokens, in_stride, d_len, d_out, out_stride, d_out_len,
+                                                                vv->d_dec_sym, vv->d_dec_off, vv->dec_ids, d_bad, d_attn);
+    ECGB_CUDA(cudaGetLastError());
+    int bad = 0;
+    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    ECGB_CUDA(cudaFreeAsync(d_bad, st));
+    if (bad) return fail(ECGB_EINVAL, "a token id is not in the vocabulary (expand_attention would raise KeyError)");
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_token_histogram(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec,
+                                    uint32_t n_ids, unsigned long long *d_counts, int device, void *stream) {
+    if (n_rec == 0) return ECGB_OK;
+    ECGB_REQUIRE(d_tokens && d_len && d_counts, "NULL buffer");
+    ECGB_REQUIRE(n_ids > 0, "n_ids is 0");
+    DeviceGuard g(device);
+    cudaStream_t st = as_stream(stream);
+    int *d_bad = nullptr;
+    ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
+    ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    int sms = 0;
+    ECGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const bool priv = n_ids <= kHistSmemIds;
+    const unsigned grid = (unsigned)std::min<size_t>(n_rec, (size_t)sms * 4);
+    if (priv) token_hist_kernel<true><<<grid, 256, 0, st>>>(d_tokens, in_stride, d_len, n_rec, n_ids, d_counts, d_bad);
+    else token_hist_kernel<false><<<grid, 256, 0, st>>>(d_tokens, in_stride, d_len, n_rec, n_ids, d_counts, d_bad);
+    ECGB_CUDA(cudaGetLastError());
+    int bad = 0;
+    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    ECGB_CUDA(cudaFreeAsync(d_bad, st));
+    if (bad) return fail(ECGB_EINVAL, "a token id is outside [0, n_ids)");
     return ECGB_OK;
 }
 

@@ -205,6 +205,20 @@ class Vocab:
                                         _ptr(sym_len), _stream(tokens.device)))
         return sym, sym_len
 
+    def expand_attention(self, tokens, lens, attn, out_stride):
+        """expand_attention (runners/interpret.py:106-111) for a batch: float32 attention per token
+        [n, stride] -> per base symbol [n, out_stride] (+ int32 lengths [n])."""
+        tokens = tokens.contiguous()
+        lens = lens.contiguous()
+        attn = attn.to(torch.float32).contiguous()
+        assert attn.shape == tokens.shape
+        n = tokens.shape[0]
+        out = torch.zeros((n, out_stride), dtype=torch.float32, device=tokens.device)
+        out_len = torch.empty((n,), dtype=torch.int32, device=tokens.device)
+        check(lib().ecgb_expand_attention(self._h, _ptr(tokens), _ptr(attn), n, tokens.shape[1], _ptr(lens), _ptr(out),
+                                          out_stride, _ptr(out_len), _stream(tokens.device)))
+        return out, out_len
+
     def encode_text(self, text):
         """One string / bytes object -> list[int] (rust_bpe.encode_text semantics)."""
         data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
@@ -224,6 +238,20 @@ class Vocab:
                 self._h = None
         except Exception:
             pass
+
+
+def token_histogram(tokens, lens, n_ids, counts=None):
+    """Counter over the encoded ids of a batch (analyze_token_distribution, tu.py:44-49): int32 CUDA
+    tokens [n, stride] + lens [n] -> int64 CUDA counts [n_ids] (accumulated into `counts` if given)."""
+    tokens = tokens.contiguous()
+    lens = lens.contiguous()
+    if counts is None:
+        counts = torch.zeros((n_ids,), dtype=torch.int64, device=tokens.device)
+    assert counts.dtype == torch.int64 and counts.numel() == n_ids and counts.is_contiguous()
+    dev = tokens.device.index if tokens.device.index is not None else torch.cuda.current_device()
+    check(lib().ecgb_token_histogram(_ptr(tokens), tokens.shape[1], _ptr(lens), tokens.shape[0], n_ids, _ptr(counts), dev,
+                                     _stream(tokens.device)))
+    return counts
 
 
 def minmax(x):

@@ -5,14 +5,17 @@ names, arguments and return values, computed by libecgbyte.so.
   process_ecg, process_large_file             tokenizer_utils.py:56-59, 79-93
   encode_text, decode_text                    tokenizer_utils.py:71-77
   save/load_vocab_and_merges                  tokenizer_utils.py:62-69
+  analyze_token_distribution                  tokenizer_utils.py:30-54
+  expand_attention                            runners/interpret.py:106-111
 """
 import pickle
+from collections import Counter
 
 import numpy as np
 import torch
 
 import rust_bpe
-from .api import Quantizer
+from .api import Quantizer, Vocab, token_histogram
 
 ALPHABET = list("abcdefghijklmnopqrstuvwxyz")
 _QUANT = {}
@@ -92,3 +95,48 @@ def encode_text(text, merges):
 
 def decode_text(encoded_ids, vocab):
     return "".join(vocab[i] for i in encoded_ids)
+
+
+def analyze_token_distribution(test_data, merges, percentiles, num_workers=None, batch=256):
+    """(token_counts: Counter, token_lengths: list[int]) over the records whose .npy paths are listed in
+    test_data (tu.py:30-54).  Records are quantised + encoded in batches on the GPU and counted there;
+    num_workers is accepted and ignored (the reference fans the files out over a process pool)."""
+    vocab = Vocab(merges)
+    n_ids = max([255] + [int(i) for _, i in merges]) + 1
+    counts = torch.zeros((n_ids,), dtype=torch.int64, device="cuda")
+    token_lengths = []
+    paths = list(test_data)
+    for s in range(0, len(paths), batch):
+        recs = [np.load(p) for p in paths[s:s + batch]]
+        shapes = {r.shape for r in recs}
+        groups = [recs] if len(shapes) == 1 else [[r] for r in recs]  # ragged shapes: one record per call
+        for g in groups:
+            x = np.ascontiguousarray(np.stack(g))
+            if x.dtype not in (np.float32, np.float64, np.int16):
+                x = x.astype(np.float64)
+            q = _quantizer(percentiles, x.dtype)
+            tokens, lens = vocab.encode_batch(q, torch.from_numpy(x).cuda())
+            token_histogram(tokens, lens, n_ids, counts)
+            token_lengths.extend(int(v) for v in lens.cpu().tolist())
+    c = counts.cpu().numpy()
+    return Counter({int(i): int(c[i]) for i in np.nonzero(c)[0]}), token_lengths
+
+
+def expand_attention(encoded_ids, attention_sequence, vocab, merges=None):
+    """runners/interpret.py:106-111: each token's attention value repeated once per symbol of the token.
+    With `merges` the expansion runs on the GPU (lengths from the vocabulary's decode table); without, the
+    lengths come from the vocab strings on the host exactly as the reference does."""
+    if merges is None:
+        out = []
+        for i, a in zip(encoded_ids, attention_sequence):
+            out.extend([a] * len(vocab[i]))
+        return out
+    n = min(len(encoded_ids), len(attention_sequence))
+    if n == 0:
+        return []
+    tok = torch.tensor(list(encoded_ids)[:n], dtype=torch.int32, device="cuda").view(1, n)
+    att = torch.tensor(list(attention_sequence)[:n], dtype=torch.float32, device="cuda").view(1, n)
+    lens = torch.tensor([n], dtype=torch.int32, device="cuda")
+    total = sum(len(vocab[int(i)]) for i in list(encoded_ids)[:n])
+    out, out_len = Vocab(merges).expand_attention(tok, lens, att, max(total, 1))
+    return out[0, : int(out_len[0])].cpu().tolist()

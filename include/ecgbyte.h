@@ -143,6 +143,18 @@ int ecgb_encode_batch_host(const ecgb_vocab *v, const ecgb_quantizer *q, const v
 int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens, size_t n_rec, size_t in_stride,
                         const int32_t *d_len, uint8_t *d_sym, size_t sym_stride, int32_t *d_sym_len,
                         void *stream);
+/* expand_attention (runners/interpret.py:106-111): one attention value per token -> one per base
+ * symbol (the value of token i repeated len(token i) times), per record; same layout rules as
+ * ecgb_decode_symbols.  (Lengths are counted in symbols; the reference counts characters of the
+ * vocab string, which differs only for raw bytes > 127 spelled "<b>".) */
+int ecgb_expand_attention(const ecgb_vocab *v, const int32_t *d_tokens, const float *d_attn, size_t n_rec,
+                          size_t in_stride, const int32_t *d_len, float *d_out, size_t out_stride,
+                          int32_t *d_out_len, void *stream);
+/* analyze_token_distribution (tokenizer_utils.py:30-54): Counter over the encoded ids of a batch.
+ * d_counts[n_ids] (u64, device) is ACCUMULATED into -- zero it first; the per-record token_lengths
+ * of the reference are the encoder's d_len.  An id outside [0, n_ids) is ECGB_EINVAL. */
+int ecgb_token_histogram(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec,
+                         uint32_t n_ids, unsigned long long *d_counts, int device, void *stream);
 /* reverse_normalize_all (tokenizer_utils.py:22-28): value = (symbol_index / 25) * ((p99+0.5) -
  * (p1-0.5)) + (p1-0.5) in float64, in that order (note 25 = len(ALPHABET) - 1, as the reference) */
 int ecgb_dequantize(double p1, double p99, const uint8_t *d_sym, size_t n, double *d_out, int device,

@@ -173,3 +173,21 @@ def prepare_training(signal_ids, question, answer, pad_to_max, pad_id, bos_id, e
         pos.append(run - 1 if m else 0)
     assert len(sample) == pad_to_max + 4
     return (np.array(sample, np.int64), np.array(mask, np.float32), np.array(labels, np.int64), np.array(pos, np.int64))
+
+
+def expand_attention(encoded_ids, attention_sequence, vocab):
+    """runners/interpret.py:106-111."""
+    out = []
+    for i, a in zip(encoded_ids, attention_sequence):
+        out.extend([a] * len(vocab[i]))
+    return out
+
+
+def token_distribution(encoded_records):
+    """tokenizer_utils.py:30-54 without the file I/O: Counter over all ids + the per-record lengths."""
+    from collections import Counter
+    counts, lengths = Counter(), []
+    for ids in encoded_records:
+        counts.update(int(i) for i in ids)
+        lengths.append(len(ids))
+    return counts, lengths

@@ -136,3 +136,84 @@ def test_global_stats_match_numpy(small_corpus):
     bad = s.copy(); bad[7] = np.nan
     assert np.isnan(percentiles(torch.from_numpy(bad).cuda(), [1])[0])
     assert all(np.isnan(v) for v in minmax(torch.from_numpy(bad).cuda()))
+
+
+def _vocab_strings(pairs):
+    vocab = {i: (chr(i) if i <= 127 else "<%d>" % i) for i in range(256)}
+    for k, (l, r) in enumerate(pairs):
+        vocab[256 + k] = vocab[int(l)] + vocab[int(r)]
+    return vocab
+
+
+def test_expand_attention_matches_restatement():
+    """runners/interpret.py:106-111 on the device vs the line-by-line restatement."""
+    from oracle import py_restatement as P
+    from ecgbyte.api import Vocab
+    from ecgbyte import tokenizer_utils as tu
+    g = np.load(GOLD)
+    v = Vocab.from_pairs(g["dec_pairs"])
+    vocab = _vocab_strings(g["dec_pairs"])
+    toks = [g["dec_tokens_%d" % r] for r in range(3)]
+    stride = max(len(t) for t in toks)
+    rng = np.random.default_rng(5)
+    tok = np.zeros((3, stride), np.int32)
+    att = rng.random((3, stride)).astype(np.float32)
+    for r, t in enumerate(toks):
+        tok[r, : len(t)] = t
+    lens = np.array([len(t) for t in toks], np.int32)
+    out, out_len = v.expand_attention(torch.from_numpy(tok).cuda(), torch.from_numpy(lens).cuda(),
+                                      torch.from_numpy(att).cuda(), 12 * 400)
+    for r in range(3):
+        want = np.array(P.expand_attention(toks[r].tolist(), att[r, : lens[r]].tolist(), vocab), np.float32)
+        assert int(out_len[r]) == len(want) == len(g["dec_text_%d" % r])
+        np.testing.assert_array_equal(out[r, : len(want)].cpu().numpy(), want)
+    # the drop-in signature, host path and device path
+    ids, a = toks[0].tolist(), att[0, : lens[0]].tolist()
+    assert tu.expand_attention(ids, a, vocab) == P.expand_attention(ids, a, vocab)
+    merges = [(list(vocab[256 + k].encode()), 256 + k) for k in range(len(g["dec_pairs"]))]
+    np.testing.assert_array_equal(np.array(tu.expand_attention(ids, a, vocab, merges), np.float32),
+                                  np.array(P.expand_attention(ids, a, vocab), np.float32))
+    # empty record, unknown id
+    z, zl = v.expand_attention(torch.zeros((1, 4), dtype=torch.int32, device="cuda"),
+                               torch.zeros((1,), dtype=torch.int32, device="cuda"),
+                               torch.zeros((1, 4), device="cuda"), 8)
+    assert int(zl[0]) == 0
+    with pytest.raises(ValueError):
+        v.expand_attention(torch.full((1, 2), 60000, dtype=torch.int32, device="cuda"),
+                           torch.tensor([2], dtype=torch.int32, device="cuda"), torch.ones((1, 2), device="cuda"), 8)
+
+
+def test_token_histogram_matches_counter(tmp_path):
+    """analyze_token_distribution (tokenizer_utils.py:30-54): Counter of encoded ids + lengths."""
+    from oracle import py_restatement as P
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Vocab, token_histogram
+    from ecgbyte import tokenizer_utils as tu
+    g = np.load(GOLD)
+    pairs = g["dec_pairs"]
+    vocab = _vocab_strings(pairs)
+    merges = [(list(vocab[256 + k].encode()), 256 + k) for k in range(len(pairs))]
+    pct = {"percentile_1": float(g["dec_pct"][0]), "percentile_99": float(g["dec_pct"][1])}
+    recs = [synth.record(3, k, 400).astype(np.float64) for k in range(5)]
+    paths = []
+    for k, r in enumerate(recs):
+        paths.append(str(tmp_path / ("r%d.npy" % k)))
+        np.save(paths[-1], r)
+    want_ids = [P.encode_text(bytes(P.normalize_all_symbols(r, pct["percentile_1"], pct["percentile_99"]).reshape(-1)), merges)
+                for r in recs]
+    want_counts, want_lengths = P.token_distribution(want_ids)
+    counts, lengths = tu.analyze_token_distribution(paths, merges, pct, num_workers=2, batch=2)
+    assert lengths == want_lengths
+    assert counts == want_counts
+    # the primitive: shared-memory counters and (large id space) global atomics give the same histogram
+    v = Vocab(merges)
+    q = Quantizer(pct, dtype=torch.float64)
+    tokens, lens = v.encode_batch(q, torch.from_numpy(np.stack(recs)).cuda())
+    n_ids = 256 + len(pairs)
+    h1 = token_histogram(tokens, lens, n_ids).cpu().numpy()
+    h2 = token_histogram(tokens, lens, 40000).cpu().numpy()
+    assert {int(i): int(h1[i]) for i in np.nonzero(h1)[0]} == dict(want_counts)
+    np.testing.assert_array_equal(h2[:n_ids], h1)
+    assert h2[n_ids:].sum() == 0
+    with pytest.raises(ValueError):
+        token_histogram(tokens, lens, 100)   # ids >= 100 occur

@@ -31,3 +31,14 @@ def test_decode_restatement_matches_reference(oracle):
         np.testing.assert_array_equal(oracle.decode(g["dec_tokens_%d" % r], merges=merges), g["dec_text_%d" % r])
         vals = P.reverse_normalize_all(sym, p1, p99).reshape(g["dec_values_%d" % r].shape)
         np.testing.assert_array_equal(vals, g["dec_values_%d" % r])
+
+
+def test_attention_and_distribution_restatements():
+    """Known answers for runners/interpret.py:106-111 and tokenizer_utils.py:30-54 (Counter + lengths)."""
+    from oracle import py_restatement as P
+    vocab = {97: "a", 98: "b", 256: "ab", 257: "abab", 200: "<200>"}
+    assert P.expand_attention([257, 97, 256], [0.5, 1.0, 2.0], vocab) == [0.5] * 4 + [1.0] + [2.0] * 2
+    assert P.expand_attention([257, 97], [0.5], vocab) == [0.5] * 4          # zip stops at the shorter input
+    assert P.expand_attention([200], [3.0], vocab) == [3.0] * 5              # characters of the vocab string
+    counts, lengths = P.token_distribution([[257, 97, 257], [], [97]])
+    assert counts == {257: 2, 97: 2} and lengths == [3, 0, 1]
