@@ -824,17 +824,86 @@ __device__ __forceinline__ Best grid_best(cg::grid_group &grid, const TrainView 
     return fin;
 }
 
+// argmax (lib.rs:92-94) for a cooperative grid; every thread returns the same winner.
+__device__ __forceinline__ Best grid_argmax(cg::grid_group &grid, const TrainView &v, Best *s_best_p) {
+    Best &s_best = *s_best_p;
+    const PairTable &t = v.main;
+    const uint64_t cap = (uint64_t)t.mask + 1;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long *tau = const_cast<unsigned long long *>(t.tau);
+    // ---- argmax (lib.rs:92-94): over the candidate list; every pair whose count is >= tau
+    //      is listed, so a listed maximum >= tau is the global one (with all its ties)
+    const unsigned long long cur_tau = *tau;
+    const uint32_t nc = *t.ncand;
+    Best mine{0, kEmptyKey, 0};
+    Best fin;
+    if (nc <= v.redundant_max) {
+        // very short list (the usual case in the long tail): every CTA scans it and reaches the same
+        // winner by itself -- no grid barrier between the histogram and the merge pass
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+            const uint32_t slot = t.cand[i];
+            const unsigned long long c = t.cnt[slot];
+            if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+        }
+        const Best b0 = block_best(mine);
+        __syncthreads();
+        if (threadIdx.x == 0) s_best = b0;
+        __syncthreads();
+        fin = s_best;
+    } else if (nc <= 8 * kTPB) {
+        // short list: block 0 scans it alone, one grid barrier publishes the winner
+        if (blockIdx.x == 0) {
+            for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+                const uint32_t slot = t.cand[i];
+                const unsigned long long c = t.cnt[slot];
+                if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+            }
+            const Best b0 = block_best(mine);
+            if (threadIdx.x == 0) v.partial[kArgmaxBlocks] = b0;
+        }
+        grid.sync();
+        fin = v.partial[kArgmaxBlocks];
+    } else {
+        for (uint64_t i = gtid; i < nc; i += gthreads) {
+            const uint32_t slot = t.cand[i];
+            const unsigned long long c = t.cnt[slot];
+            if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
+        }
+        fin = grid_best(grid, v, mine, &s_best);
+    }
+    if (fin.count == 0 || fin.count < cur_tau) {
+        // the list is exhausted: full scan for the true maximum, then rebuild the list with
+        // a lower threshold (counts only decay, so this happens O(log) times per run)
+        mine = Best{0, kEmptyKey, 0};
+        for (uint64_t s = gtid; s < cap; s += gthreads) {
+            const uint32_t k = t.keys[s];
+            if (k == kEmptyKey) continue;
+            const unsigned long long c = t.cnt[s];
+            if (c != 0) mine = better(mine, Best{c, k, 1});
+        }
+        fin = grid_best(grid, v, mine, &s_best);
+        const unsigned long long new_tau = fin.count - fin.count / 4 > 0 ? fin.count - fin.count / 4 : 1;
+        if (gtid == 0) { *tau = new_tau; *t.ncand = 0; }
+        for (uint64_t w = gtid; w < (cap + 31) / 32; w += gthreads) t.inbits[w] = 0;
+        grid.sync();
+        for (uint64_t s = gtid; s < cap; s += gthreads) {
+            if (t.keys[s] == kEmptyKey || t.cnt[s] < new_tau) continue;
+            atomicOr(&t.inbits[s >> 5], 1u << (s & 31));
+            t.cand[atomicAdd(t.ncand, 1u)] = (uint32_t)s;
+        }
+        grid.sync();
+    }
+    return fin;
+}
+
 __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32_t n_steps) {
     cg::grid_group grid = cg::this_grid();
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
     extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
     bool res_mode = false, res_fresh = false;
-    const PairTable &t = v.main;
-    const uint64_t cap = (uint64_t)t.mask + 1;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
-    unsigned long long *tau = const_cast<unsigned long long *>(t.tau);
     ECGB_MARK_DECL;
     uint32_t step = 0;
     for (; step < n_steps; step++) {
@@ -856,68 +925,7 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
                 __syncthreads();
             }
         }
-        // ---- argmax (lib.rs:92-94): over the candidate list; every pair whose count is >= tau
-        //      is listed, so a listed maximum >= tau is the global one (with all its ties)
-        const unsigned long long cur_tau = *tau;
-        const uint32_t nc = *t.ncand;
-        Best mine{0, kEmptyKey, 0};
-        Best fin;
-        if (nc <= v.redundant_max) {
-            // very short list (the usual case in the long tail): every CTA scans it and reaches the same
-            // winner by itself -- no grid barrier between the histogram and the merge pass
-            for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
-                const uint32_t slot = t.cand[i];
-                const unsigned long long c = t.cnt[slot];
-                if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
-            }
-            const Best b0 = block_best(mine);
-            __syncthreads();
-            if (threadIdx.x == 0) s_best = b0;
-            __syncthreads();
-            fin = s_best;
-        } else if (nc <= 8 * kTPB) {
-            // short list: block 0 scans it alone, one grid barrier publishes the winner
-            if (blockIdx.x == 0) {
-                for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
-                    const uint32_t slot = t.cand[i];
-                    const unsigned long long c = t.cnt[slot];
-                    if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
-                }
-                const Best b0 = block_best(mine);
-                if (threadIdx.x == 0) v.partial[kArgmaxBlocks] = b0;
-            }
-            grid.sync();
-            fin = v.partial[kArgmaxBlocks];
-        } else {
-            for (uint64_t i = gtid; i < nc; i += gthreads) {
-                const uint32_t slot = t.cand[i];
-                const unsigned long long c = t.cnt[slot];
-                if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
-            }
-            fin = grid_best(grid, v, mine, &s_best);
-        }
-        if (fin.count == 0 || fin.count < cur_tau) {
-            // the list is exhausted: full scan for the true maximum, then rebuild the list with
-            // a lower threshold (counts only decay, so this happens O(log) times per run)
-            mine = Best{0, kEmptyKey, 0};
-            for (uint64_t s = gtid; s < cap; s += gthreads) {
-                const uint32_t k = t.keys[s];
-                if (k == kEmptyKey) continue;
-                const unsigned long long c = t.cnt[s];
-                if (c != 0) mine = better(mine, Best{c, k, 1});
-            }
-            fin = grid_best(grid, v, mine, &s_best);
-            const unsigned long long new_tau = fin.count - fin.count / 4 > 0 ? fin.count - fin.count / 4 : 1;
-            if (gtid == 0) { *tau = new_tau; *t.ncand = 0; }
-            for (uint64_t w = gtid; w < (cap + 31) / 32; w += gthreads) t.inbits[w] = 0;
-            grid.sync();
-            for (uint64_t s = gtid; s < cap; s += gthreads) {
-                if (t.keys[s] == kEmptyKey || t.cnt[s] < new_tau) continue;
-                atomicOr(&t.inbits[s >> 5], 1u << (s & 31));
-                t.cand[atomicAdd(t.ncand, 1u)] = (uint32_t)s;
-            }
-            grid.sync();
-        }
+        const Best fin = grid_argmax(grid, v, &s_best);
         if (gtid == 0) {
             v.best[step] = fin;
             if (fin.count == 0) atomicMin(&v.dev->done_step, step);
@@ -963,6 +971,49 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
         uint16_t *dst = v.tok[step & 1] + pre;
         for (int i = threadIdx.x; i < cn; i += kTPB) dst[i] = chunk[i];
         if (blockIdx.x == 0 && threadIdx.x == 0) v.dev->n[step & 1] = all;
+    }
+}
+
+// Sharded training: the argmax of one step as a cooperative launch (candidate list instead of a full
+// table scan), then this shard's boundary record for the winning pair, as argmax_kernel leaves it.
+__global__ void __launch_bounds__(kTPB, 4) dist_argmax_kernel(TrainView v, uint32_t step) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Best s_best;
+    const Best fin = grid_argmax(grid, v, &s_best);
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    // boundary record of this shard for the winning pair (warp 0 of CTA 0)
+    const uint16_t *tok = v.tok[step & 1];
+    const unsigned long long n = v.dev->n[step & 1];
+    const uint32_t a = fin.key >> 16, bb = fin.key & 0xFFFFu;
+    const int lane = threadIdx.x;
+    unsigned long long run = 0;
+    const bool xx = fin.count != 0 && a == bb && v.world > 1;
+    if (xx) {  // trailing run of a, 32 tokens per probe
+        bool hit = false;
+        long long found = -1;
+        for (long long p = (long long)n - 1; p >= 0 && !hit; p -= 32) {
+            const long long q = p - lane;
+            const bool nonx = q >= 0 && tok[q] != a;
+            const unsigned m = __ballot_sync(0xffffffffu, nonx);
+            if (m) { found = p - (__ffs(m) - 1); hit = true; }
+        }
+        run = (unsigned long long)((long long)n - 1 - found);
+    }
+    if (lane == 0) {
+        v.best[step] = fin;
+        if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+        Boundary bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.n_lo = (uint32_t)n;
+        bd.n_hi = (uint32_t)(n >> 32);
+        for (int i = 0; i < 3; i++) bd.first[i] = (unsigned long long)i < n ? (uint32_t)tok[i] : kSentinel;
+        bd.last[1] = n >= 1 ? (uint32_t)tok[n - 1] : kSentinel;
+        bd.last[0] = n >= 2 ? (uint32_t)tok[n - 2] : kSentinel;
+        if (xx) {
+            bd.trail_par = (uint32_t)(run & 1);
+            bd.all_a = run == n ? 1u : 0u;
+        }
+        *v.boundary = bd;
     }
 }
 
@@ -1022,9 +1073,11 @@ struct ecgb_trainer {
     void *blocks[32] = {nullptr};
     int n_blocks = 0;
     uint32_t *d_list = nullptr;  // this rank's delta list
+    int coop_grid = 0;           // grid of dist_argmax_kernel (all CTAs co-resident)
 };
 
 static int dev_alloc(ecgb_trainer *t, void **p, size_t bytes, bool zero) {
+    if (t->n_blocks >= (int)(sizeof(t->blocks) / sizeof(t->blocks[0]))) return fail(ECGB_ECUDA, "trainer allocation table full");
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
     if (e != cudaSuccess) return fail(ECGB_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     t->blocks[t->n_blocks++] = *p;
@@ -1384,7 +1437,23 @@ extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const vo
     const uint32_t list_words = 4 + 3 * t->list_cap;
     apply_lists_kernel<<<t->sms, 256, 0, st>>>(t->v.main, static_cast<const uint32_t *>(d_all_lists), list_words,
                                                t->list_cap, t->v.world);
-    argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
+    static const bool full_scan = getenv("ECGB_DIST_FULLSCAN") != nullptr;  // A/B knob: the old full-table argmax
+    if (full_scan) {
+        argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
+    } else {
+    if (t->coop_grid == 0) {
+        int per_sm = 0;
+        ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_argmax_kernel, kTPB, 0));
+        if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "dist_argmax_kernel does not fit on this device");
+        t->coop_grid = std::min(t->sms * std::min(per_sm, 4), kArgmaxBlocks);
+    }
+    {
+        TrainView view = t->v;
+        view.redundant_max = kRedundantArgmax;
+        void *kargs[] = {&view, &step};
+        ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)dist_argmax_kernel, dim3(t->coop_grid), dim3(kTPB), kargs, 0, st));
+    }
+    }
     ECGB_CUDA(cudaGetLastError());
     ECGB_CUDA(cudaMemcpyAsync(d_boundary_out, t->v.boundary, sizeof(Boundary), cudaMemcpyDeviceToDevice, st));
     t->argmax_for = step + 1;
