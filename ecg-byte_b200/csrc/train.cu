@@ -88,7 +88,11 @@ struct DevState {
     unsigned long long n[2];  // token count of buffer 0 / 1
     uint32_t done_step;       // first step that found no pair (0xFFFFFFFF = none)
     uint32_t argmax_done;     // block completion counter of argmax_kernel (self-resetting)
+    uint32_t cur_step;        // device-side step counter (ECGB_STEP_DEVICE: whole steps replayed from a CUDA graph)
+    uint32_t max_steps;       // = max_merges: steps beyond it are ignored
 };
+constexpr uint32_t kStepFromDevice = 0xFFFFFFFFu;
+static_assert(kStepFromDevice == ECGB_STEP_DEVICE, "header constant");
 
 struct TrainView {
     uint16_t *tok[2];
@@ -800,6 +804,8 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
 __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step, const Boundary *__restrict__ all_bd,
                                                      PairTable upd) {
     __shared__ MergeSmem sm;
+    if (step == kStepFromDevice) step = v.dev->cur_step;
+    if (step >= v.dev->max_steps) return;
     const Best bb = v.best[step];
     if (bb.count == 0) return;  // no pair left (lib.rs:88-90); done_step was recorded by argmax_kernel
     merge_pass<true, false>(v, step, bb, all_bd, upd, sm, nullptr);
@@ -979,6 +985,8 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
 __global__ void __launch_bounds__(kTPB, 4) dist_argmax_kernel(TrainView v, uint32_t step) {
     cg::grid_group grid = cg::this_grid();
     __shared__ Best s_best;
+    if (step == kStepFromDevice) step = v.dev->cur_step;
+    if (step > v.dev->max_steps) return;  // uniform over the grid
     const Best fin = grid_argmax(grid, v, &s_best);
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     // boundary record of this shard for the winning pair (warp 0 of CTA 0)
@@ -1036,6 +1044,8 @@ __global__ void compact_delta_kernel(PairTable d, uint32_t *list, uint32_t cap) 
     }
 }
 
+__global__ void advance_step_kernel(DevState *dev) { dev->cur_step++; }
+
 __global__ void reset_list_kernel(uint32_t *list, uint32_t *used) { list[0] = 0; list[1] = 0; list[2] = 0; list[3] = 0; *used = 0; }
 
 __global__ void apply_lists_kernel(PairTable main, const uint32_t *__restrict__ lists, uint32_t list_words, uint32_t cap,
@@ -1074,6 +1084,7 @@ struct ecgb_trainer {
     int n_blocks = 0;
     uint32_t *d_list = nullptr;  // this rank's delta list
     int coop_grid = 0;           // grid of dist_argmax_kernel (all CTAs co-resident)
+    bool device_steps = false;   // steps were issued with ECGB_STEP_DEVICE
 };
 
 static int dev_alloc(ecgb_trainer *t, void **p, size_t bytes, bool zero) {
@@ -1166,7 +1177,7 @@ extern "C" int ecgb_trainer_destroy(ecgb_trainer *t) {
 
 static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
     DevState h{};
-    h.n[0] = n; h.n[1] = 0; h.done_step = 0xFFFFFFFFu; h.argmax_done = 0;
+    h.n[0] = n; h.n[1] = 0; h.done_step = 0xFFFFFFFFu; h.argmax_done = 0; h.cur_step = 0; h.max_steps = t->max_merges;
     ECGB_CUDA(cudaMemcpyAsync(t->v.dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     ECGB_CUDA(cudaStreamSynchronize(st));  // h is a stack object
     const size_t cap = (size_t)t->v.main.mask + 1;
@@ -1189,6 +1200,7 @@ static int reset_state(ecgb_trainer *t, uint64_t n, cudaStream_t st) {
     ECGB_CUDA(cudaMemsetAsync(t->v.tile_status, 0, 8 * ((size_t)(t->capacity / kTile) + 2), st));
     t->steps_done = 0;
     t->argmax_for = 0;
+    t->device_steps = false;
     t->loaded = true;
     return ECGB_OK;
 }
@@ -1431,7 +1443,8 @@ extern "C" int ecgb_trainer_dist_count(ecgb_trainer *t, const void *d_all_bounda
 extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const void *d_all_lists, void *d_boundary_out,
                                         void *stream) {
     ECGB_REQUIRE(t && d_all_lists && d_boundary_out, "NULL argument");
-    ECGB_REQUIRE(step <= t->max_merges, "step %u out of range", step);
+    ECGB_REQUIRE(step == kStepFromDevice || step <= t->max_merges, "step %u out of range", step);
+    ECGB_REQUIRE(step != kStepFromDevice || getenv("ECGB_DIST_FULLSCAN") == nullptr, "the full-scan argmax has no device-side step");
     DeviceGuard g(t->device);
     cudaStream_t st = as_stream(stream);
     const uint32_t list_words = 4 + 3 * t->list_cap;
@@ -1456,7 +1469,8 @@ extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const vo
     }
     ECGB_CUDA(cudaGetLastError());
     ECGB_CUDA(cudaMemcpyAsync(d_boundary_out, t->v.boundary, sizeof(Boundary), cudaMemcpyDeviceToDevice, st));
-    t->argmax_for = step + 1;
+    if (step == kStepFromDevice) t->device_steps = true;
+    else t->argmax_for = step + 1;
     return ECGB_OK;
 }
 
@@ -1465,7 +1479,7 @@ extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const vo
 extern "C" int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const void *d_all_boundaries, void *d_list_out,
                                        void *stream) {
     ECGB_REQUIRE(t && d_all_boundaries && d_list_out, "NULL argument");
-    ECGB_REQUIRE(step < t->max_merges, "step %u out of range", step);
+    ECGB_REQUIRE(step == kStepFromDevice || step < t->max_merges, "step %u out of range", step);
     DeviceGuard g(t->device);
     cudaStream_t st = as_stream(stream);
     uint32_t *list = static_cast<uint32_t *>(d_list_out);
@@ -1474,7 +1488,18 @@ extern "C" int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const voi
     merge_kernel<<<merge_grid, kTPB, 0, st>>>(t->v, step, static_cast<const Boundary *>(d_all_boundaries), t->v.delta);
     compact_delta_kernel<<<t->sms * 2, 256, 0, st>>>(t->v.delta, list, t->list_cap);
     ECGB_CUDA(cudaGetLastError());
-    t->steps_done = step + 1;
+    if (step == kStepFromDevice) t->device_steps = true;
+    else t->steps_done = step + 1;
+    return ECGB_OK;
+}
+
+// Advance the device-side step counter (the last node of a captured step).
+extern "C" int ecgb_trainer_dist_advance(ecgb_trainer *t, void *stream) {
+    ECGB_REQUIRE(t, "NULL argument");
+    DeviceGuard g(t->device);
+    advance_step_kernel<<<1, 1, 0, as_stream(stream)>>>(t->v.dev);
+    ECGB_CUDA(cudaGetLastError());
+    t->device_steps = true;
     return ECGB_OK;
 }
 
@@ -1489,7 +1514,11 @@ extern "C" int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t 
     if (rc) return rc;
     DevState hs;
     ECGB_CUDA(cudaMemcpy(&hs, t->v.dev, sizeof(hs), cudaMemcpyDeviceToHost));
-    const uint32_t done = std::min(n_steps, hs.done_step);
+    if (t->device_steps) {  // steps were driven by the device-side counter
+        t->steps_done = std::min(hs.cur_step, t->max_merges);
+        t->argmax_for = t->steps_done;
+    }
+    const uint32_t done = std::min(std::min(n_steps, hs.done_step), t->device_steps ? t->steps_done : n_steps);
     t->steps_done = std::min(t->steps_done, done);
     std::vector<Best> hb(done ? done : 1);
     if (done) ECGB_CUDA(cudaMemcpy(hb.data(), t->v.best, sizeof(Best) * done, cudaMemcpyDeviceToHost));

@@ -74,6 +74,7 @@ def _declare(L):
         "ecgb_trainer_dist_count": ([vp, vp, vp, vp], i32),
         "ecgb_trainer_dist_commit": ([vp, u32, vp, vp, vp], i32),
         "ecgb_trainer_dist_merge": ([vp, u32, vp, vp, vp], i32),
+        "ecgb_trainer_dist_advance": ([vp, vp], i32),
         "ecgb_trainer_results": ([vp, u32, vp, vp, vp, C.POINTER(u32)], i32),
         "ecgb_expand_merges": ([vp, u32, vp, u64, vp], i32),
     }

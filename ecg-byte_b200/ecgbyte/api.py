@@ -368,6 +368,8 @@ def expand_merges(pairs):
 class Trainer:
     """byte_pair_encoding (lib.rs:58-125) on one device (or one shard of a corpus)."""
 
+    STEP_DEVICE = 0xFFFFFFFF  # dist_commit / dist_merge: step number from the device-side counter
+
     def __init__(self, capacity_tokens, max_merges, device=None, table_log2=0):
         self.device = _dev_index(device)
         self.max_merges = int(max_merges)
@@ -450,6 +452,10 @@ class Trainer:
     def dist_merge(self, step, all_boundaries, list_out):
         check(lib().ecgb_trainer_dist_merge(self._h, step, _ptr(all_boundaries), _ptr(list_out),
                                             _stream(list_out.device)))
+
+    def dist_advance(self, device):
+        """Increment the device-side step counter (see STEP_DEVICE)."""
+        check(lib().ecgb_trainer_dist_advance(self._h, _stream(device)))
 
     def results(self, n_steps):
         m = int(n_steps)

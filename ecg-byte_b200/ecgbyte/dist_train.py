@@ -18,7 +18,17 @@ merged across record boundaries.  Here rank g owns a contiguous piece of that st
 The two exchanges per step are all-gathers of small fixed-size device buffers
 (NCCL over NVLink through torch.distributed); everything else is on-device and
 asynchronous.  With world == 1 this degenerates to the single-device loop.
+
+The step number lives in a counter on the device (Trainer.STEP_DEVICE), so every step issues
+the same calls with the same arguments and one step can be captured in a CUDA graph (kernels
+and both all-gathers) and replayed for the remaining merges -- one graph launch per merge
+instead of ~8 launches and two Python-level collectives.  Measured on 2 B200s the step is bound
+by the device (kernels ~45 us + two all-gathers), not by the host: 13.1 k merges/s replayed vs
+12.9 k eager, so the NCCL path stays eager unless ECGB_DIST_GRAPH=1; the single-process variant
+(train_shards_local), where the Python loop over the ranks does dominate, replays by default.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -38,10 +48,17 @@ class TorchExchange:
         self.dist.all_gather_into_tensor(out, inp, group=self.group)
 
 
-def train_shard(shard, num_merges, exchange=None, device=None, table_log2=0, check_every=0):
+def _graph_default(default):
+    v = os.environ.get("ECGB_DIST_GRAPH")
+    return default if v is None else v != "0"
+
+
+def train_shard(shard, num_merges, exchange=None, device=None, table_log2=0, check_every=0, use_graph=None):
     """shard: this rank's piece of the corpus (bytes / numpy uint8 / uint8 CUDA tensor).
     Returns (pairs [m,2], counts [m], ntied [m], trainer); identical on every rank."""
     ex = exchange or TorchExchange()
+    if use_graph is None:
+        use_graph = _graph_default(False)
     n = shard.numel() if isinstance(shard, torch.Tensor) else len(shard)
     tr = Trainer(max(n, 1), num_merges, device=device, table_log2=table_log2)
     tr.load(shard)
@@ -56,16 +73,44 @@ def train_shard(shard, num_merges, exchange=None, device=None, table_log2=0, che
         ex.all_gather(all_bnd, bnd)
         tr.dist_count(all_bnd, lst)
         ex.all_gather(all_lst, lst)
-        for step in range(num_merges):
-            tr.dist_commit(step, all_lst, bnd)
+        S = Trainer.STEP_DEVICE
+
+        def one_step():
+            tr.dist_commit(S, all_lst, bnd)
             ex.all_gather(all_bnd, bnd)
-            tr.dist_merge(step, all_bnd, lst)
+            tr.dist_merge(S, all_bnd, lst)
             ex.all_gather(all_lst, lst)
+            tr.dist_advance(dev)
+
+        _run_steps(one_step, num_merges, dev, use_graph)
         pairs, counts, ntied = tr.results(num_merges)
     return pairs, counts, ntied, tr
 
 
-def train_shards_local(shards, num_merges, device=None, table_log2=0):
+def _run_steps(one_step, num_merges, dev, use_graph, warm=3):
+    """`warm` eager steps (lazy initialisation: NCCL channels, occupancy queries), then -- if allowed --
+    one captured step replayed for the rest."""
+    eager = min(num_merges, warm)
+    for _ in range(eager):
+        one_step()
+    left = num_merges - eager
+    if left <= 0:
+        return
+    graph = None
+    if use_graph:
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):  # capturing does not execute the step
+            one_step()
+    if graph is not None:
+        for _ in range(left):
+            graph.replay()
+    else:
+        for _ in range(left):
+            one_step()
+
+
+def train_shards_local(shards, num_merges, device=None, table_log2=0, use_graph=None):
     """The same protocol with every 'rank' living in this process on ONE device (the
     all-gathers become concatenations).  Used to test the sharded kernels on a single GPU."""
     world = len(shards)
@@ -91,13 +136,21 @@ def train_shards_local(shards, num_merges, device=None, table_log2=0):
         for r, t in enumerate(trs):
             t.dist_count(all_bnd, nlst[r * lbytes:(r + 1) * lbytes])
         all_lst.copy_(nlst)
-        for step in range(num_merges):
+        S = Trainer.STEP_DEVICE
+        nb = [nbnd[r * bbytes:(r + 1) * bbytes] for r in range(world)]
+        nl = [nlst[r * lbytes:(r + 1) * lbytes] for r in range(world)]
+
+        def one_step():
             for r, t in enumerate(trs):
-                t.dist_commit(step, all_lst, nbnd[r * bbytes:(r + 1) * bbytes])
+                t.dist_commit(S, all_lst, nb[r])
             all_bnd.copy_(nbnd)
             for r, t in enumerate(trs):
-                t.dist_merge(step, all_bnd, nlst[r * lbytes:(r + 1) * lbytes])
+                t.dist_merge(S, all_bnd, nl[r])
             all_lst.copy_(nlst)
+            for t in trs:
+                t.dist_advance(dev)
+
+        _run_steps(one_step, num_merges, dev, _graph_default(True) if use_graph is None else use_graph)
         res = [t.results(num_merges) for t in trs]
     del bnd, lst
     return res, trs

@@ -240,7 +240,13 @@ int ecgb_trainer_histogram(ecgb_trainer *t, uint32_t *h_pairs, int64_t *h_counts
  *   results()                          -> merges, counts, tie log
  *
  * Every rank applies the same lists in the same order, so the histograms -- and the
- * argmax -- are identical without any reduction. */
+ * argmax -- are identical without any reduction.
+ *
+ * step = ECGB_STEP_DEVICE in dist_commit / dist_merge: take the step number from a counter on the
+ * device, which ecgb_trainer_dist_advance increments.  The calls of one step then have constant
+ * arguments, so commit / all-gather / merge / all-gather / advance can be captured once in a CUDA
+ * graph and replayed per merge (ecgbyte/dist_train.py); replays beyond max_merges do nothing. */
+#define ECGB_STEP_DEVICE 0xFFFFFFFFu
 int ecgb_trainer_dist_sizes(const ecgb_trainer *t, uint32_t *boundary_bytes, uint32_t *list_bytes);
 int ecgb_trainer_dist_begin(ecgb_trainer *t, int rank, int world, void *d_boundary_out, void *stream);
 int ecgb_trainer_dist_count(ecgb_trainer *t, const void *d_all_boundaries, void *d_list_out, void *stream);
@@ -248,6 +254,7 @@ int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const void *d_all_l
                              void *stream);
 int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const void *d_all_boundaries, void *d_list_out,
                             void *stream);
+int ecgb_trainer_dist_advance(ecgb_trainer *t, void *stream);
 int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t *h_pairs, uint64_t *h_counts,
                          uint32_t *h_ntied, uint32_t *n_done);
 

@@ -124,12 +124,12 @@ def test_train_config1_scale_matches_fixture():
     assert h == want
 
 
-def _check_sharded(oracle, text, cuts, m):
+def _check_sharded(oracle, text, cuts, m, use_graph=True):
     from ecgbyte.dist_train import train_shards_local
     text = np.ascontiguousarray(text, np.uint8)
     bounds = [0] + list(cuts) + [len(text)]
     shards = [text[bounds[r]:bounds[r + 1]].tobytes() for r in range(len(bounds) - 1)]
-    res, trs = train_shards_local(shards, m)
+    res, trs = train_shards_local(shards, m, use_graph=use_graph)  # graph: one captured step, replayed
     o_ids, o_pairs, o_counts, o_ntied = oracle.train_pairs(text, m, fast=len(text) > 20000)
     for pairs, counts, ntied in res:  # every rank reports the same merges
         np.testing.assert_array_equal(pairs, o_pairs)
@@ -146,6 +146,7 @@ def test_sharded_training_one_gpu_many_ranks(oracle, small_corpus):
     rng = np.random.default_rng(4)
     text = rng.integers(97, 100, size=5000).astype(np.uint8)
     _check_sharded(oracle, text, [1700, 3300], 60)
+    _check_sharded(oracle, text, [1700, 3300], 60, use_graph=False)   # eager loop, same device-side step counter
     _check_sharded(oracle, text, [0, 1, 2, 4999], 40)          # empty and single-token shards
     runs = np.concatenate([np.full(4100, 105, np.uint8), rng.integers(104, 107, size=50).astype(np.uint8),
                            np.full(8300, 105, np.uint8), np.array([106, 105, 105], np.uint8)])
