@@ -6,15 +6,17 @@
 //
 // Here, per step, ONE streaming pass over the token stream (2-byte ids, read once,
 // written once -- the algorithmic 2*(n_t + n_{t+1}) bytes of SURVEY.md 8d):
-//   * merge_kernel: tiles of 4096 tokens, dynamic tile tickets, decoupled look-back for
-//     the output offsets; every merge site also patches the pair histogram for the
-//     windows it destroys/creates (warp-aggregated atomics into an open-addressing hash
+//   * merge_pass: tiles of 4096 tokens, decoupled look-back for the output offsets; every
+//     merge site also patches the pair histogram for the windows it destroys/creates
+//     (block-private shared-memory table, flushed once per CTA into an open-addressing hash
 //     table in global memory/L2), so the histogram always equals a full recount and no
 //     second pass over the tokens is needed;
-//   * argmax_kernel: one scan of the hash table with the deterministic tie rule
-//     (max count, then smallest (left,right)); the last block to finish folds the
-//     per-block partials and records the winner on the device -- the host never
-//     synchronises inside the loop.
+//   * argmax with the deterministic tie rule (max count, then smallest (left,right)) over a
+//     candidate list (every slot whose count is >= tau), falling back to a table scan that
+//     lowers tau when the list runs dry.
+// One device: train_loop_kernel runs every step inside ONE persistent cooperative kernel; once
+// the stream fits in the CTAs' shared memory it stays there (resident tail: each CTA owns a
+// chunk and treats the other CTAs exactly like the ranks of a sharded run).
 // (x,x) pairs: merge() is greedy left to right, so inside a run of x only the elements
 // at even run offsets start a site (lib.rs:14-18).  A tile finds the offset of its first
 // element by scanning backwards to the start of the run that enters it.
@@ -183,12 +185,6 @@ __device__ __forceinline__ void patch_clear(PatchTable &p) {
 __device__ __forceinline__ void patch_flush(PatchTable &p, const PairTable &t, unsigned long long tau_val) {
     for (int i = threadIdx.x; i < kPatchSlots; i += blockDim.x)
         if (p.keys[i] != kEmptyKey && p.vals[i] != 0) table_add(t, p.keys[i], (long long)p.vals[i], tau_val);
-}
-
-// All 32 lanes call; lanes with the same key are folded into one atomic.
-__device__ __forceinline__ void warp_patch_add(PatchTable &p, const PairTable &t, bool valid, uint32_t key, int delta) {
-    const unsigned m = __match_any_sync(0xffffffffu, valid ? key : kEmptyKey);
-    if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) patch_add(p, t, key, delta * __popc(m));
 }
 
 __device__ __forceinline__ uint32_t mk(uint32_t l, uint32_t r) { return (l << 16) | r; }
