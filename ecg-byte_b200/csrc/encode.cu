@@ -42,6 +42,10 @@ struct EncArgs {
 };
 
 constexpr uint32_t kNoClass = 31u;
+// The rings hold SHIFT CODES, 31 - class: `mask << code` moves the symbol's edge bit to bit 31 (the
+// match test is a sign test) and the lower classes above bit 31 - class (one more shift and a POPC give
+// the child rank).  The sentinel class 31 is code 0; bit 31 of a child bitmap is never set.
+constexpr uint32_t kNoCode = 31u - kNoClass;
 
 // ---- 16-sample groups: the unit a walker loads, quantises and appends to its ring ----
 template <int DT> struct ElemOf { using T = typename SampleTraits<DT>::In; };
@@ -85,12 +89,12 @@ __device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_to
             q = CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
                       : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
         }
-        w[k >> 2] |= q << ((k & 3) * 8);
+        w[k >> 2] |= (31u - q) << ((k & 3) * 8);
     }
-    if (valid < kGroup) {  // the record ends inside (or before) this group
+    if (valid < kGroup) {  // the record ends inside (or before) this group: sentinel code 0
 #pragma unroll
         for (int k = 0; k < kGroup; k++)
-            if (k >= valid) w[k >> 2] |= kNoClass << ((k & 3) * 8);  // classes are < 32: OR gives 31
+            if (k >= valid) w[k >> 2] &= ~(0xFFu << ((k & 3) * 8));
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -206,13 +210,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
     int32_t hi32 = 0;   // ring holds [max(hi32 - R, 0), hi32) and never drops symbols >= mpos
     uint32_t mask = root.x, base = root_base, mid = 0, cnt = 0;
     int32_t *outp = nullptr;
-    sts_u8(ring, kNoClass);  // idle lanes sit on a sentinel
+    sts_u8(ring, kNoCode);  // idle lanes sit on a sentinel
 
     for (;;) {
         // ------------------------------------------------ phase boundary (convergent)
         // (1) walkers parked on a class-31 symbol at the root: end of record, or a byte that
         //     occurs in no merge and is its own token (text only; lib.rs:155-157)
-        while (active && base == root_base && pos32 < hi32 && lds_u8(ring_addr<R>(ring, pos32)) == kNoClass) {
+        while (active && base == root_base && pos32 < hi32 && lds_u8(ring_addr<R>(ring, pos32)) == kNoCode) {
             if (pos32 >= end32) {
                 a.lens[r_cur] = (int32_t)cnt;
                 active = false;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
                 pos32 = mpos = hi32 = end32 = 0;
                 mask = root.x;
                 base = root_base;
-                sts_u8(ring, kNoClass);
+                sts_u8(ring, kNoCode);
             }
         }
         if (__all_sync(FULL, done)) break;
@@ -312,16 +316,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
             // The symbol of the next step is loaded one step ahead (ring[pos + 1], speculating on a
             // match) and the symbol at the restart point is remembered when a terminal is passed, so
             // no shared-memory load sits on the step-to-step dependency chain.
-            uint32_t c = lds_u8(ring_addr<R>(ring, pos32));  // symbol at pos32
-            uint32_t cm = lds_u8(ring_addr<R>(ring, mpos));  // symbol at mpos
+            uint32_t c = lds_u8(ring_addr<R>(ring, pos32));  // shift code of the symbol at pos32
+            uint32_t cm = lds_u8(ring_addr<R>(ring, mpos));  // ... at mpos
 #pragma unroll 2
             for (; K > 0; K--) {
                 const int32_t adv = pos32 + 1;
                 const uint32_t cspec = lds_u8(ring_addr<R>(ring, adv));
-                const uint32_t bit = 1u << c;  // the sentinel (31) never has an edge
-                const bool okm = (mask & bit) != 0;
+                const uint32_t sh = mask << c;  // edge bit of the symbol at bit 31; the sentinel never has one
+                const bool okm = (int32_t)sh < 0;
                 // a failed step re-reads the root, which is also the state a new token starts from
-                const uint32_t idx = okm ? base + __popc(mask & (bit - 1u)) : 0u;
+                const uint32_t idx = okm ? base + __popc(sh << 1) : 0u;
                 const uint2 nd = node_at(idx);
                 const bool emit = !okm && base != root_base;  // walk ended: emit the longest terminal
                 if (emit && cnt < stride) outp[cnt] = (int32_t)mid;
