@@ -136,3 +136,19 @@ def test_record_sharding_covers_everything():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_model_many_shards(oracle):
+    """The resident tail of the single-device trainer runs this protocol with one shard per CTA (hundreds of
+    small chunks, some of them emptied by the merges): many shards, long (x,x) runs across many of them."""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        n = int(rng.integers(150, 400))
+        text = rng.integers(97, 100, size=n).astype(np.uint8).tolist()
+        lo = int(rng.integers(0, n - 60))
+        text[lo:lo + 57] = [97] * 57                      # a run of x over ~6 shards
+        world = int(rng.integers(24, 40))
+        cuts = sorted(int(c) for c in rng.integers(0, n + 1, size=world - 1))
+        check_against_oracle(oracle, text, cuts, int(rng.integers(20, 60)))
+    even = [i * 10 for i in range(1, 30)]                 # equal chunks, as at the switch to the resident tail
+    check_against_oracle(oracle, ([97] * 7 + [98, 97, 97, 99]) * 28, even, 40)
