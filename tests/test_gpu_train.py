@@ -71,6 +71,20 @@ def test_train_ecg_corpus(oracle, small_corpus):
     _compare(oracle, sym, 600)
 
 
+def test_train_resident_tail_dense_steps(oracle):
+    """6e6 symbols fit the CTAs' shared memory from the first step (chunks of three tiles): the dense early
+    merges, (x,x) steps included, all run through the resident in-place pass."""
+    from ecgbyte import synth
+    x = np.stack([synth.record(11, k, 5000) for k in range(100)])
+    pct = synth.BENCH_PERCENTILES
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    _compare(oracle, sym, 250)
+    # a little over the limit: the first steps stream, then the switch happens mid-run
+    x2 = np.stack([synth.record(12, k, 5000) for k in range(140)])
+    sym2 = oracle.quantize(x2, pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    _compare(oracle, sym2, 120)
+
+
 def test_train_table_overflow_is_loud(oracle):
     from ecgbyte import EcgbError
     rng = np.random.default_rng(2)
