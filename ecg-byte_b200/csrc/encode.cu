@@ -89,13 +89,16 @@ __device__ __forceinline__ uint4 fetch16(const void *base, size_t g, size_t n_to
             q = CELLS ? classify<Thr>(s, sf, lo, scale, static_cast<const QuantSmem<Thr> *>(qsmem))
                       : classify_search<Thr>(s, static_cast<const Thr *>(thr_smem));
         }
-        w[k >> 2] |= (31u - q) << ((k & 3) * 8);
+        w[k >> 2] |= q << ((k & 3) * 8);
     }
-    if (valid < kGroup) {  // the record ends inside (or before) this group: sentinel code 0
+    if (valid < kGroup) {  // the record ends inside (or before) this group
 #pragma unroll
         for (int k = 0; k < kGroup; k++)
-            if (k >= valid) w[k >> 2] &= ~(0xFFu << ((k & 3) * 8));
+            if (k >= valid) w[k >> 2] |= kNoClass << ((k & 3) * 8);  // classes are < 32: OR gives 31
     }
+    // classes -> shift codes, four at a time (every byte is <= 31: no borrow between bytes)
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = 0x1F1F1F1Fu - w[j];
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
