@@ -42,3 +42,13 @@ def test_attention_and_distribution_restatements():
     assert P.expand_attention([200], [3.0], vocab) == [3.0] * 5              # characters of the vocab string
     counts, lengths = P.token_distribution([[257, 97, 257], [], [97]])
     assert counts == {257: 2, 97: 2} and lengths == [3, 0, 1]
+
+
+def test_expand_attention_mirror_host_path():
+    """The drop-in signature (runners/interpret.py:106-111) without merges runs on the host, like the reference."""
+    from oracle import py_restatement as P
+    from ecgbyte import tokenizer_utils as tu
+    vocab = {97: "a", 98: "b", 256: "ab", 257: "abab"}
+    ids, att = [257, 97, 256, 98], [0.25, 1.0, 2.0, 4.0]
+    assert tu.expand_attention(ids, att, vocab) == P.expand_attention(ids, att, vocab)
+    assert tu.expand_attention([], [], vocab) == []
