@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libecgbyte.so")
-SOURCES = ["common.cu", "quantize.cu", "vocab.cu", "encode.cu", "train.cu", "post.cu", "stats.cu", "encode_long.cu"]
+SOURCES = ["common.cu", "quantize.cu", "vocab.cu", "pairtab.cu", "encode.cu", "encode2.cu", "train.cu", "post.cu", "stats.cu", "encode_long.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",

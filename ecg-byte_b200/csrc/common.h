@@ -63,6 +63,14 @@ struct QuantTables {
     int exact_cells;            // 1: the cell table is usable; 0: fall back to d_thr search
 };
 
+// device image of the pair table (trie_host.h); d_ent == nullptr when the vocabulary has none
+struct PairView {
+    const uint32_t *d_ent;
+    const uint16_t *d_tok;
+    const uint8_t *d_cls;   // byte -> class, SE for bytes without one
+    uint32_t n_ent, root_base, W, SM, SE;
+};
+
 struct VocabView {
     const uint2 *d_nodes;   // compact nodes: x = child mask (bit c = class c), y = base << 16 | (token + 1)
     uint32_t n_nodes;
@@ -76,6 +84,7 @@ struct VocabView {
     const uint8_t *d_dec_sym;
     const uint32_t *d_dec_off;
     uint32_t dec_ids;       // ids 0 .. dec_ids-1 are covered by d_dec_off
+    PairView pair;
 };
 
 }  // namespace ecgb
@@ -88,6 +97,13 @@ struct ecgb_quantizer {
     ecgb::QuantTables tab;
     void *d_block;  // one allocation holding all tables
 };
+
+namespace ecgb {
+// encode2.cu: the pair-table walker; ECGB_EUNSUPPORTED = take the bitmap-trie kernel instead
+int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact_cells, const void *d_in, size_t n_total,
+                   size_t n_rec, size_t rec_len, const uint64_t *d_offsets, int32_t *d_tokens, size_t out_stride,
+                   int32_t *d_len, int device, cudaStream_t st);
+}  // namespace ecgb
 
 const ecgb::VocabView *ecgb_vocab_view(const ecgb_vocab *v);
 // one long string, parallel over positions (encode_long.cu); compact vocabularies, n < 2^32

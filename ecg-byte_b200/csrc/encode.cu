@@ -448,6 +448,11 @@ extern "C" int ecgb_encode_symbols(const ecgb_vocab *v, const uint8_t *d_sym, si
         ECGB_CUDA(cudaGetLastError());
         return ECGB_OK;
     }
+    {
+        const int rc2 = launch_encode2(ECGB_U8, vv, nullptr, 1, d_sym, n_rec * rec_len, n_rec, rec_len, d_offsets, d_tokens,
+                                       out_stride, d_len, device, st);
+        if (rc2 != ECGB_EUNSUPPORTED) return rc2;
+    }
     EncArgs a{};
     a.in = d_sym;
     a.n_total = n_rec * rec_len;  // with explicit offsets the kernel uses offsets[n_rec]
@@ -477,6 +482,11 @@ extern "C" int ecgb_encode_batch(const ecgb_vocab *v, const ecgb_quantizer *q, c
         if (rc == ECGB_OK) rc = ecgb_encode_symbols(v, d_sym, n_rec, rec_len, nullptr, d_tokens, out_stride, d_len, stream);
         cudaFreeAsync(d_sym, st);
         return rc;
+    }
+    {
+        const int rc2 = launch_encode2((int)q->dtype, vv, &q->tab, q->tab.exact_cells, d_in, n_rec * rec_len, n_rec, rec_len, nullptr,
+                                       d_tokens, out_stride, d_len, device, st);
+        if (rc2 != ECGB_EUNSUPPORTED) return rc2;
     }
     EncArgs a{};
     a.in = d_in; a.n_total = n_rec * rec_len;

@@ -1,0 +1,488 @@
+// E2: encode_text (reference: rust_bpe/src/lib.rs:149-193) fused with Q1
+// (tokenizer_utils.py:14-19) for sm_100a -- the two-symbols-per-step walker.
+//
+// Semantics: greedy longest match over the trie -- at each token start walk as far as symbols
+// match, remember the longest terminal seen, emit it and restart right after it
+// (lib.rs:163-190).  This is NOT rank-ordered BPE merging.
+//
+// Mapping: one walker = one thread = one record, one CTA of up to 768 walkers per SM; the record
+// axis alone fills the chip.  What a walker steps through is the PAIR TABLE (trie_host.h): a
+// double-array automaton whose states are the trie nodes at even depth, so ONE 4-byte
+// shared-memory gather advances a walker by TWO symbols (the round-1 kernel paid an 8-byte gather
+// and a POPC rank per symbol; its l1tex pipe was 86 % busy).  A warp alternates between convergent
+// phases:
+//   refill : every lane with room streams the next 16 samples of ITS record with 256-bit loads
+//            (LDG.E.ENL2.256: one full 32-byte sector per lane per request -- half the l1tex
+//            wavefronts of 128-bit loads, profiles/micro/loadpat.cu), classifies them (K1's
+//            arithmetic) and appends 16 PAIR CODES to its private ring in shared memory: entry p is
+//            the table offset of the symbol pair (p-1, p), so a step needs one LDS.U16 and one add
+//            to form the probe address.  Rings are transposed per warp (bank = lane), so ring
+//            traffic is conflict-free wherever each cursor is.
+//   walk   : bursts of kBurst branch-free pair steps (probe, compare the stored code, adopt the
+//            next state; a lane whose probe fails just stops for the rest of the burst), then ONE
+//            convergent block that serves every lane that failed: the odd-length probe
+//            (first symbol alone), token id fetch, append to the lane's token queue, restart at
+//            the root.  Tokens leave through the queue as 16-byte stores, eight per flush.
+//   The end of a record is a sentinel class that matches nothing; record switches and bytes that are
+//   their own token (text input) are handled at the phase boundary, outside the hot loop.  A ring
+//   holds 64 symbols; a walk that runs further than that past its last terminal (flat-line tokens
+//   of 128-256 symbols) simply lets the refill overwrite its history, and if the token then ends
+//   before the oldest entry still in the ring, the walker REWINDS: the ring restarts at the new
+//   token start and those few symbols are read a second time (about four times per record).
+// HBM traffic is the algorithmic minimum: samples once, tokens once.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "quant_device.cuh"
+
+#ifndef ECGB_ENC_BURST
+#define ECGB_ENC_BURST 4
+#endif
+
+namespace ecgb {
+
+struct Enc2Args {
+    const void *in;            // samples (or text bytes), all records back to back
+    size_t n_total;            // total samples in `in`
+    size_t n_rec, rec_len;
+    const uint64_t *offsets;   // optional [n_rec + 1]
+    int32_t *tokens;
+    size_t out_stride;
+    int32_t *lens;
+    PairView pv;
+    uint32_t vec_out;          // token rows are 16-byte aligned: flush with 128-bit stores
+    uint32_t in_al32;          // `in` is 32-byte aligned: 256-bit loads
+    QuantTables qt;
+};
+
+constexpr int kG2 = 16;          // symbols per refill
+constexpr int kRing2 = 64;       // ring capacity in symbols (128 bytes per lane)
+constexpr int kBurst = ECGB_ENC_BURST;
+constexpr int kMaxBursts = 8;    // bursts per walk phase (at most one token per burst: the queue cannot overflow)
+constexpr int kThreads2 = 768;
+constexpr uint32_t kRingWarpBytes = 32u * kRing2 * 2u;
+constexpr uint32_t kQueueWarpBytes = 32u * 32u;
+constexpr uint32_t kCheck = 0x3FFCu;  // the code field of a table entry
+
+template <int DT> struct Elem2 { using T = typename SampleTraits<DT>::In; using Thr = typename SampleTraits<DT>::Thr; };
+template <> struct Elem2<ECGB_U8> { using T = uint8_t; using Thr = float; };
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// ring entry of symbol position p, addressed by q2 = 2 * p: halfword (p & 63) of the lane's ring,
+// 32-bit words transposed inside the warp's 4 KB-aligned region (word w of lane l at (w * 32 + l) * 4)
+__device__ __forceinline__ uint32_t ring_at2(uint32_t ring_lane, int32_t q2) {
+    return ring_lane + (((uint32_t)q2 & 124u) << 5) + ((uint32_t)q2 & 2u);
+}
+// two entries further (one pair step): the word index lives in address bits 7..11
+__device__ __forceinline__ uint32_t ring_next(uint32_t ra) {
+    return ((ra + 128u) & 0xF80u) | (ra & ~0xF80u);  // one LOP3
+}
+// token queue slot of token number t (16 halfwords per lane, transposed the same way)
+__device__ __forceinline__ uint32_t queue_at(uint32_t queue_lane, uint32_t t) {
+    return queue_lane + ((t & 14u) << 6) + ((t & 1u) << 1);
+}
+
+// 32 bytes at p (32-byte aligned when al32)
+__device__ __forceinline__ void ldg32B(const void *p, bool al32, uint32_t (&r)[8]) {
+    if (al32) {
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "l"(p));
+    } else {
+        const uint4 a = __ldg(static_cast<const uint4 *>(p)), b = __ldg(static_cast<const uint4 *>(p) + 1);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+    }
+}
+
+// class << 2 of one sample (K1's arithmetic: quant_device.cuh)
+template <int DT, bool CELLS>
+__device__ __forceinline__ uint32_t class4_of(typename Elem2<DT>::T v, float lo, float scale, uint32_t cell_sa,
+                                              const void *thr_smem, uint32_t cls_sa) {
+    using Thr = typename Elem2<DT>::Thr;
+    if constexpr (DT == ECGB_U8) {
+        uint32_t c;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(cls_sa + (uint32_t)v));
+        return c;  // the staged table already holds class << 2
+    } else if constexpr (CELLS) {
+        float sf;
+        const Thr s = to_thr(v, &sf);
+        const uint32_t cell = cell_of(sf, lo, scale);
+        Thr t;
+        if constexpr (sizeof(Thr) == 4) {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(cell_sa + cell * 4u));
+        } else {
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(cell_sa + cell * 8u));
+        }
+        return cell * 4u + (s >= t ? 4u : 0u);
+    } else {
+        float sf;
+        const Thr s = to_thr(v, &sf);
+        return classify_search<Thr>(s, static_cast<const Thr *>(thr_smem)) << 2;
+    }
+}
+
+// 16 samples at global element index g (g % 16 == 0) -> 16 pair codes appended to the ring at symbol
+// position p0 (p0 % 16 == 0).  Positions at or beyond `valid` are the sentinel.  prev = class << 2
+// of the symbol before p0 (in/out).
+template <int DT, bool CELLS>
+__device__ __forceinline__ void refill16(const void *base, size_t g, size_t n_total, int valid, bool al32, uint32_t ring_lane,
+                                         int32_t p0, uint32_t &prev, uint32_t wmul, uint32_t se4, float lo, float scale,
+                                         uint32_t cell_sa, const void *thr_smem, uint32_t cls_sa) {
+    using T = typename Elem2<DT>::T;
+    constexpr int NB = sizeof(T) * 16 / 32;  // 32-byte pieces (u8: half a piece)
+    T e[16];
+    const T *p = static_cast<const T *>(base) + g;
+    if (g + 16 <= n_total) {
+        if constexpr (NB >= 1) {
+            uint32_t r[NB][8];
+#pragma unroll
+            for (int j = 0; j < NB; j++) ldg32B(reinterpret_cast<const uint8_t *>(p) + 32 * j, al32, r[j]);
+            memcpy(e, r, sizeof(e));
+        } else {
+            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+            memcpy(e, &r, sizeof(e));
+        }
+    } else {  // ragged end of the buffer
+#pragma unroll
+        for (int k = 0; k < 16; k++) e[k] = (g + k < n_total) ? p[k] : T(0);
+    }
+    uint32_t cs[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) cs[k] = class4_of<DT, CELLS>(e[k], lo, scale, cell_sa, thr_smem, cls_sa);
+    if (valid < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (k >= valid) cs[k] = se4;
+    }
+    const uint32_t wa = ring_lane + (((uint32_t)p0 & (uint32_t)(kRing2 - 1)) << 6);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t d0 = prev * wmul + cs[2 * j];
+        const uint32_t d1 = cs[2 * j] * wmul + cs[2 * j + 1];
+        prev = cs[2 * j + 1];
+        sts32(wa + 128u * j, d0 | (d1 << 16));
+    }
+}
+
+template <int DT, bool CELLS, bool TOKS>
+__global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
+    using Thr = typename Elem2<DT>::Thr;
+    extern __shared__ __align__(16) uint8_t smem[];
+    // layout: [pad to 4 KB] rings | queues | ent | tok | aux
+    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t pad = (0u - smem_sa) & 4095u;
+    uint8_t *s_rings = smem + pad;
+    uint8_t *s_queues = s_rings + nwarps * kRingWarpBytes;
+    const uint32_t n_ent = a.pv.n_ent;
+    const uint32_t ent_bytes = (n_ent * 4u + 15u) & ~15u;
+    const uint32_t tok_bytes = TOKS ? ((n_ent * 2u + 15u) & ~15u) : 0u;
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(s_queues + nwarps * kQueueWarpBytes);
+    uint16_t *s_tok = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(s_ent) + ent_bytes);
+    uint8_t *s_aux = reinterpret_cast<uint8_t *>(s_ent) + ent_bytes + tok_bytes;
+    // aux: quantiser cell table + threshold list (sample dtypes) or the byte -> class << 2 table (text)
+    QuantSmem<Thr> *qs = reinterpret_cast<QuantSmem<Thr> *>(s_aux);
+    Thr *s_thr = reinterpret_cast<Thr *>(s_aux + sizeof(QuantSmem<Thr>));
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(s_ent);
+    const uint32_t tok_sa = (uint32_t)__cvta_generic_to_shared(s_tok);
+    const uint32_t cell_sa = (uint32_t)__cvta_generic_to_shared(qs);
+    const uint32_t cls_sa = (uint32_t)__cvta_generic_to_shared(s_aux);
+    const uint32_t ring_lane = smem_sa + pad + warp * kRingWarpBytes + lane * 4u;
+    const uint32_t queue_lane = (uint32_t)__cvta_generic_to_shared(s_queues) + warp * kQueueWarpBytes + lane * 4u;
+
+    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) s_ent[i] = a.pv.d_ent[i];
+    if (TOKS)
+        for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) s_tok[i] = a.pv.d_tok[i];
+    if constexpr (DT == ECGB_U8) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_aux[i] = (uint8_t)(a.pv.d_cls[i] << 2);
+    } else {
+        load_quant_smem(qs, a.qt);
+        if (threadIdx.x < kNumThresholds) s_thr[threadIdx.x] = static_cast<const Thr *>(a.qt.d_thr)[threadIdx.x];
+    }
+    // rings start out as zeros: a stale entry is always a harmless table offset
+    for (uint32_t i = threadIdx.x; i < nwarps * (kRingWarpBytes + kQueueWarpBytes) / 4u; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_rings)[i] = 0u;
+    __syncthreads();
+
+    const float qlo = a.qt.lo, qscale = a.qt.scale;
+    const uint32_t W = a.pv.W;
+    const uint32_t wmul = 1u << W;
+    const uint32_t sm_code = a.pv.SM << 2;  // low field of the odd-length ("single") probe
+    const uint32_t se4 = a.pv.SE << 2;      // sentinel class, scaled
+    const uint32_t himask = (wmul - 1u) << (W + 2u);
+    const uint32_t lomask = (wmul - 1u) << 2;
+    const uint32_t rootA = tab_sa + a.pv.root_base * 4u;
+    const uint32_t stride = a.out_stride < 0x7fffffffu ? (uint32_t)a.out_stride : 0x7fffffffu;
+    const bool al32 = a.in_al32 != 0;
+    const bool vec_out = a.vec_out != 0;
+    const size_t n_total = a.offsets ? (size_t)a.offsets[a.n_rec] : a.n_total;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    // contiguous, even split of the records over the CTAs
+    const size_t r_lo = (size_t)(((unsigned __int128)a.n_rec * blockIdx.x) / gridDim.x);
+    const size_t r_hi = (size_t)(((unsigned __int128)a.n_rec * (blockIdx.x + 1)) / gridDim.x);
+    size_t r_next = r_lo + threadIdx.x;
+
+    // walker state; positions are relative to `org` (a multiple of the refill group)
+    bool active = false, done = false, parked = false, rewind = false, closed = false;
+    size_t org = 0, r_cur = 0;
+    int32_t end32 = 0;   // record end
+    int32_t hi32 = 0;    // the ring holds the entries of positions [hi32 - kRing2, hi32)
+    int32_t q = 0;       // 2 * position of the next symbol to read
+    int32_t mq = 0;      // 2 * position the ring should keep: start of the pair that set `m`, or of the walk
+    uint32_t A = rootA;  // shared-memory address of the current state's row
+    uint32_t ra = ring_lane;  // ring address of the entry at the cursor (pair (q/2, q/2 + 1))
+    uint32_t cw = 0;     // ... and the entry
+    uint32_t m = 0;      // last probe that passed a terminal: probe address << 8 | low byte of its entry
+    uint32_t cnt = 0, flushed = 0, prev = se4;
+    int32_t *outp = nullptr;
+
+    auto tok_of = [&](uint32_t ref) -> uint32_t {  // token id of the slot at shared address `ref`
+        const uint32_t off2 = (ref - tab_sa) >> 1;
+        if (TOKS) return lds16(tok_sa + off2);
+        return (uint32_t)__ldg(a.pv.d_tok + (off2 >> 1));
+    };
+    auto drain = [&]() {  // every queued token, one by one (record ends, rare paths)
+        for (uint32_t t = flushed; t < cnt; t++)
+            if (t < stride) outp[t] = (int32_t)lds16(queue_at(queue_lane, t));
+        flushed = cnt;
+    };
+
+    for (;;) {
+        // ------------------------------------------------ phase boundary (convergent)
+        // (1) parked walkers
+        if (parked) {
+            const int32_t pos = q >> 1;
+            if (rewind) {
+                // the token ended before the oldest entry still in the ring: restart the ring there
+                const int32_t shift = pos & ~(kG2 - 1);
+                org += (size_t)shift;
+                end32 -= shift;
+                q = mq = 2 * (pos - shift);
+                hi32 = 0;
+                closed = false;
+                prev = se4;
+                rewind = false;
+            } else {
+                // end of the record, or a byte that occurs in no merge and is its own token
+                // (text only; lib.rs:155-157)
+                drain();
+                if (pos >= end32) {
+                    a.lens[r_cur] = (int32_t)cnt;
+                    active = false;
+                } else {
+                    const uint32_t byte = static_cast<const uint8_t *>(a.in)[org + (size_t)pos];
+                    if (cnt < stride) outp[cnt] = (int32_t)byte;
+                    cnt++;
+                    flushed = cnt;
+                    q += 2;
+                    mq = q;
+                    m = 0;
+                    A = rootA;
+                }
+            }
+            parked = false;
+        }
+        // (2) next record
+        if (!active && !done) {
+            if (r_next < r_hi) {
+                r_cur = r_next;
+                r_next += blockDim.x;
+                const size_t rs = a.offsets ? (size_t)a.offsets[r_cur] : r_cur * a.rec_len;
+                const size_t re = a.offsets ? (size_t)a.offsets[r_cur + 1] : rs + a.rec_len;
+                org = rs & ~(size_t)(kG2 - 1);
+                end32 = (int32_t)(re - org);
+                q = mq = 2 * (int32_t)(rs - org);
+                hi32 = 0;
+                closed = false;
+                A = rootA;
+                m = 0;
+                cnt = flushed = 0;
+                prev = se4;
+                outp = a.tokens + r_cur * a.out_stride;
+                active = true;
+            } else {
+                done = true;
+                A = rootA;
+                cw = 0;
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+        // (3) token queues: eight tokens at a time as two 16-byte stores
+        {
+            const bool fl = active && cnt - flushed >= 8u;
+            if (__any_sync(FULL, fl)) {
+                if (fl) {
+                    const uint32_t qa = queue_lane + ((flushed & 8u) << 6);
+                    const uint32_t w0 = lds32(qa), w1 = lds32(qa + 128u), w2 = lds32(qa + 256u), w3 = lds32(qa + 384u);
+                    if (vec_out && flushed + 8u <= stride) {
+                        int4 *dst = reinterpret_cast<int4 *>(outp + flushed);
+                        dst[0] = make_int4((int)(w0 & 0xFFFFu), (int)(w0 >> 16), (int)(w1 & 0xFFFFu), (int)(w1 >> 16));
+                        dst[1] = make_int4((int)(w2 & 0xFFFFu), (int)(w2 >> 16), (int)(w3 & 0xFFFFu), (int)(w3 >> 16));
+                    } else {
+                        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (flushed + k < stride) outp[flushed + k] = (int32_t)((w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                    }
+                    flushed += 8u;
+                }
+            }
+        }
+        // (4) refill, 16 symbols at a time: while the ring still keeps everything from mq on, or --
+        //     when the walker cannot run a burst otherwise -- over its own history (see `rewind`)
+#pragma unroll 1
+        for (int g = 0; g < kRing2 / kG2; g++) {
+            const bool room = hi32 - (mq >> 1) <= kRing2 - kG2 - 2;
+            const bool starved = hi32 - (q >> 1) < 2 * kBurst;
+            const bool want = active && !closed && (room || starved);
+            if (!__any_sync(FULL, want)) break;
+            if (want) {
+                refill16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, al32, ring_lane, hi32, prev, wmul, se4, qlo,
+                                    qscale, cell_sa, s_thr, cls_sa);
+                hi32 += kG2;
+                if (hi32 >= end32) {
+                    // the record is complete: two entries of sentinel close it (a walker never steps
+                    // past them, so nothing more is needed)
+                    sts32(ring_lane + (((uint32_t)hi32 & (kRing2 - 1)) << 6), (prev * wmul + se4) | ((se4 * wmul + se4) << 16));
+                    hi32 += 2;
+                    closed = true;
+                }
+            }
+        }
+        // ------------------------------------------------ walk
+        uint32_t nb = 0x7fffffffu;
+        if (active && !closed) nb = (uint32_t)(hi32 - (q >> 1)) / (2u * kBurst);
+        uint32_t K = min(__reduce_min_sync(FULL, nb), (uint32_t)kMaxBursts);
+        ra = ring_at2(ring_lane, q + 2);
+        cw = lds16(ra);
+        bool walk = active;
+        for (; K > 0; K--) {
+            bool run = walk;
+#pragma unroll
+            for (int j = 0; j < kBurst; j++) {
+                const uint32_t addr = A + cw;
+                const uint32_t e = lds32(addr);
+                const uint32_t ran = ring_next(ra);
+                const bool ok = run && ((e ^ cw) & kCheck) == 0u;
+                if (ok && (e & 3u) != 0u) { m = __byte_perm(e, addr, 0x6540); mq = q; }
+                if (ok) { A = tab_sa + (e >> 14); q += 4; ra = ran; cw = lds16(ran); }
+                run = ok;
+            }
+            const bool f = walk && !run;
+            if (__any_sync(FULL, f)) {
+                if (f) {
+                    // the pair at the cursor is no edge: the first symbol alone may still reach a token
+                    const uint32_t x1 = (cw & himask) | sm_code;
+                    const uint32_t addr1 = A + x1;
+                    const uint32_t e1 = lds32(addr1);
+                    uint32_t ref = 0;
+                    int32_t nq = 0;
+                    bool got = true;
+                    if (((e1 ^ x1) & kCheck) == 0u) { ref = addr1; nq = q + 2; }
+                    else if (m & 2u) { ref = m >> 8; nq = mq + 4; }
+                    else if (m & 1u) { ref = (m >> 8) - (m & lomask) + sm_code; nq = mq + 2; }
+                    else got = false;  // sentinel at the root: end of record, or a byte that is its own token
+                    if (got) {
+                        sts16(queue_at(queue_lane, cnt), tok_of(ref));
+                        cnt++;
+                        q = mq = nq;
+                        m = 0;
+                        A = rootA;
+                        if ((nq >> 1) + 1 < hi32 - kRing2) {  // the restart point has left the ring
+                            parked = rewind = true;
+                            walk = false;
+                        } else {
+                            ra = ring_at2(ring_lane, q + 2);
+                            cw = lds16(ra);
+                        }
+                    } else {
+                        parked = true;
+                        walk = false;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int DT>
+static int launch_encode2_t(const Enc2Args &a, int exact_cells, int device, cudaStream_t st) {
+    using Thr = typename Elem2<DT>::Thr;
+    const int sms = sm_count(device);
+    int smem_max = 0;
+    ECGB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // tables + quantiser cells (or the byte -> class table) + slack to align the rings to 4 KB
+    const size_t aux = (DT == ECGB_U8 ? 256 : ((sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32 + 15) & ~(size_t)15)) + 4096;
+    const size_t ent_bytes = ((size_t)a.pv.n_ent * 4 + 15) & ~(size_t)15;
+    const size_t tok_bytes = ((size_t)a.pv.n_ent * 2 + 15) & ~(size_t)15;
+    const size_t per_warp = kRingWarpBytes + kQueueWarpBytes;
+    if ((size_t)smem_max < ent_bytes + aux + per_warp) return ECGB_EUNSUPPORTED;  // caller falls back (no message)
+    // one walker per record; CTAs get equal contiguous record ranges
+    size_t grid = std::min<size_t>((size_t)sms, (a.n_rec + 31) / 32);
+    if (grid < 1) grid = 1;
+    const size_t per_cta = (a.n_rec + grid - 1) / grid;
+    static const int knob = getenv("ECGB_ENC_WARPS") ? atoi(getenv("ECGB_ENC_WARPS")) : 0;  // tuning knob
+    const size_t warps_max = knob > 0 ? (size_t)knob : (size_t)kThreads2 / 32;
+    // token ids in shared memory when that leaves at least 16 warps of walkers, else in L2
+    const size_t fit_tok = (size_t)smem_max > ent_bytes + tok_bytes + aux ? ((size_t)smem_max - ent_bytes - tok_bytes - aux) / per_warp : 0;
+    const size_t fit_notok = ((size_t)smem_max - ent_bytes - aux) / per_warp;
+    const bool toks = fit_tok >= std::min<size_t>(16, warps_max);
+    const size_t cap = std::min(warps_max, toks ? fit_tok : fit_notok);
+    if (cap < 1) return ECGB_EUNSUPPORTED;
+    // as few passes over the CTA's records as the walker limit allows, lanes spread evenly over them
+    const size_t passes = (per_cta + cap * 32 - 1) / (cap * 32);
+    const size_t w = std::max<size_t>(1, std::min(cap, ((per_cta + passes - 1) / passes + 31) / 32));
+    const size_t smem = ent_bytes + (toks ? tok_bytes : 0) + aux + w * per_warp;
+    auto kern = exact_cells ? (toks ? encode2_kernel<DT, true, true> : encode2_kernel<DT, true, false>)
+                            : (toks ? encode2_kernel<DT, false, true> : encode2_kernel<DT, false, false>);
+    ECGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, (unsigned)(w * 32), smem, st>>>(a);
+    ECGB_CUDA(cudaGetLastError());
+    return ECGB_OK;
+}
+
+// Fused quantise + encode (dt = sample type) or encode of text bytes (dt = ECGB_U8) through the pair
+// table.  ECGB_EUNSUPPORTED (without a message) when the vocabulary has no pair table or it does
+// not fit in shared memory: the caller then takes the bitmap-trie kernel.
+int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact_cells, const void *d_in, size_t n_total,
+                   size_t n_rec, size_t rec_len, const uint64_t *d_offsets, int32_t *d_tokens, size_t out_stride,
+                   int32_t *d_len, int device, cudaStream_t st) {
+    if (!vv->pair.d_ent) return ECGB_EUNSUPPORTED;
+    if (rec_len >= (1ull << 30)) return ECGB_EUNSUPPORTED;
+    // A/B knobs: ECGB_ENCODE_V1 forces the round-1 bitmap-trie kernel, ECGB_ENCODE_V2 this one
+    static const bool off = getenv("ECGB_ENCODE_V1") != nullptr || getenv("ECGB_ENCODE_V2") == nullptr;
+    if (off) return ECGB_EUNSUPPORTED;
+    Enc2Args a{};
+    a.in = d_in; a.n_total = n_total; a.n_rec = n_rec; a.rec_len = rec_len; a.offsets = d_offsets;
+    a.tokens = d_tokens; a.out_stride = out_stride; a.lens = d_len;
+    a.pv = vv->pair;
+    a.vec_out = (((uintptr_t)d_tokens & 15) == 0 && (out_stride & 3) == 0) ? 1u : 0u;
+    a.in_al32 = ((uintptr_t)d_in & 31) == 0 ? 1u : 0u;
+    if (qt) a.qt = *qt;
+    switch (dt) {
+        case ECGB_F32: return launch_encode2_t<ECGB_F32>(a, exact_cells, device, st);
+        case ECGB_F64: return launch_encode2_t<ECGB_F64>(a, exact_cells, device, st);
+        case ECGB_I16: return launch_encode2_t<ECGB_I16>(a, exact_cells, device, st);
+        case ECGB_U8: return launch_encode2_t<ECGB_U8>(a, 1, device, st);
+    }
+    return ECGB_EUNSUPPORTED;
+}
+
+}  // namespace ecgb

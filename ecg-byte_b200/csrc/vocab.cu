@@ -17,36 +17,7 @@
 #include <vector>
 
 #include "common.h"
-
-namespace ecgb {
-
-struct HostNode {
-    std::map<uint32_t, int> child;  // ordered by symbol
-    int64_t token = -1;
-};
-
-struct HostTrie {
-    std::vector<HostNode> nodes;
-    uint32_t max_len = 1;
-    int insert(const uint32_t *seq, size_t len, uint32_t id) {
-        int n = 0;
-        for (size_t i = 0; i < len; i++) {
-            auto it = nodes[n].child.find(seq[i]);
-            if (it == nodes[n].child.end()) {
-                nodes.emplace_back();
-                int c = (int)nodes.size() - 1;
-                nodes[n].child[seq[i]] = c;
-                n = c;
-            } else {
-                n = it->second;
-            }
-        }
-        nodes[n].token = id;  // lib.rs:145: later insert overwrites
-        return n;
-    }
-};
-
-}  // namespace ecgb
+#include "trie_host.h"
 
 struct ecgb_vocab {
     int device = 0;
@@ -56,6 +27,9 @@ struct ecgb_vocab {
     uint8_t *d_cls = nullptr;
     uint8_t *d_dec_sym = nullptr;
     uint32_t *d_dec_off = nullptr;
+    uint32_t *d_pair_ent = nullptr;  // pair table (trie_host.h), NULL when the vocabulary does not fit it
+    uint16_t *d_pair_tok = nullptr;
+    uint8_t *d_pair_cls = nullptr;
     uint8_t h_cls[256];
     // host copy of the expanded sequences (decode, pickles)
     std::vector<uint32_t> seq;
@@ -77,38 +51,19 @@ extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_of
     if (rc) return rc;
 
     HostTrie t;
-    t.nodes.reserve(1024 + (size_t)n_merges * 4);
-    t.nodes.emplace_back();
-    for (uint32_t b = 0; b < 256; b++) t.insert(&b, 1, b);  // lib.rs:155-157
-    for (uint32_t i = 0; i < n_merges; i++) {               // lib.rs:159-161
-        uint64_t o = h_seq_off[i], e = h_seq_off[i + 1];
-        ECGB_REQUIRE(e >= o, "seq_off is not non-decreasing at merge %u", i);
-        ECGB_REQUIRE(e > o, "merge %u has an empty sequence", i);
-        for (uint64_t k = o; k < e; k++)
-            ECGB_REQUIRE(h_seq[k] < 256, "merge %u: sequence element %u is not a byte", i, h_seq[k]);
-        t.insert(h_seq + o, (size_t)(e - o), h_ids[i]);
-        t.max_len = std::max<uint32_t>(t.max_len, (uint32_t)(e - o));
+    {
+        const int bad = build_host_trie(&t, h_seq, h_seq_off, h_ids, n_merges);
+        ECGB_REQUIRE(bad == 0, "merge %d is malformed (empty sequence, or an element that is not a byte)", bad - 1);
     }
 
     // ---- symbol classes: a..z -> 0..25, other bytes that need a trie edge -> 26.. ----
-    bool needs[256] = {false};
-    for (size_t n = 0; n < t.nodes.size(); n++) {
-        for (auto &kv : t.nodes[n].child) {
-            const HostNode &c = t.nodes[kv.second];
-            if (n != 0) needs[kv.first] = true;                              // edge below depth 1
-            else if (!c.child.empty() || c.token != (int64_t)kv.first) needs[kv.first] = true;
-        }
-    }
+    uint8_t cls_all[256];
+    int n_classes = 0;
+    vocab_classes(t, cls_all, &n_classes);
+    // the bitmap nodes hold up to 31 classes (class 31 = none)
+    bool compact = n_classes <= 31;
     uint8_t cls[256];
-    std::memset(cls, 31, sizeof(cls));
-    for (int k = 0; k < kNumSymbols; k++) cls['a' + k] = (uint8_t)k;
-    int n_classes = kNumSymbols;
-    bool compact = true;
-    for (int b = 0; b < 256; b++) {
-        if (!needs[b] || (b >= 'a' && b <= 'z')) continue;
-        if (n_classes >= 31) { compact = false; break; }
-        cls[b] = (uint8_t)n_classes++;
-    }
+    for (int b = 0; b < 256; b++) cls[b] = cls_all[b] < 31 ? cls_all[b] : (uint8_t)31;
     int64_t max_tok = 255;
     for (auto &nd : t.nodes) max_tok = std::max(max_tok, nd.token);
     if (max_tok >= 0xFFFF) compact = false;
@@ -212,6 +167,34 @@ extern "C" int ecgb_vocab_create(const uint32_t *h_seq, const uint64_t *h_seq_of
     v->view.ecg_alphabet = 1;  // classes 0..25 are always 'a'..'z' in the compact layout
     v->view.max_token_len = t.max_len;
 
+    // ---- pair table: the two-symbol-stride automaton the fused encoder walks (trie_host.h) ----
+    {
+        PairTab pt;
+        if (build_pairtab(t, cls_all, n_classes, &pt)) {
+            uint8_t pcls[256];
+            for (int b = 0; b < 256; b++) pcls[b] = cls_all[b] < n_classes ? cls_all[b] : (uint8_t)pt.SE;
+            cudaError_t e4 = cudaMalloc((void **)&v->d_pair_ent, pt.ent.size() * 4);
+            if (e4 == cudaSuccess) e4 = cudaMalloc((void **)&v->d_pair_tok, pt.tok.size() * 2 + 16);
+            if (e4 == cudaSuccess) e4 = cudaMalloc((void **)&v->d_pair_cls, 256);
+            if (e4 == cudaSuccess) e4 = cudaMemcpy(v->d_pair_ent, pt.ent.data(), pt.ent.size() * 4, cudaMemcpyHostToDevice);
+            if (e4 == cudaSuccess) e4 = cudaMemcpy(v->d_pair_tok, pt.tok.data(), pt.tok.size() * 2, cudaMemcpyHostToDevice);
+            if (e4 == cudaSuccess) e4 = cudaMemcpy(v->d_pair_cls, pcls, 256, cudaMemcpyHostToDevice);
+            if (e4 != cudaSuccess) {
+                ecgb_vocab_destroy(v);
+                return fail(e4 == cudaErrorMemoryAllocation ? ECGB_ENOMEM : ECGB_ECUDA, "pair table upload failed: %s", cudaGetErrorString(e4));
+            }
+            v->view.pair.d_ent = v->d_pair_ent;
+            v->view.pair.d_tok = v->d_pair_tok;
+            v->view.pair.d_cls = v->d_pair_cls;
+            v->view.pair.n_ent = (uint32_t)pt.ent.size();
+            v->view.pair.root_base = pt.root_base;
+            v->view.pair.W = pt.W;
+            v->view.pair.SM = pt.SM;
+            v->view.pair.SE = pt.SE;
+            v->info.pair_slots = (uint32_t)pt.ent.size();
+        }
+    }
+
     // ---- decode tables: id -> expanded bytes (a later merge with the same id wins, like a dict) ----
     {
         uint32_t max_id = 255;
@@ -256,6 +239,9 @@ extern "C" int ecgb_vocab_destroy(ecgb_vocab *v) {
         cudaFree(v->d_cls);
         cudaFree(v->d_dec_sym);
         cudaFree(v->d_dec_off);
+        cudaFree(v->d_pair_ent);
+        cudaFree(v->d_pair_tok);
+        cudaFree(v->d_pair_cls);
     }
     delete v;
     return ECGB_OK;

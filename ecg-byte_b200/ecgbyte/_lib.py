@@ -27,7 +27,7 @@ class PackCfg(C.Structure):
 
 class VocabInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
-        "n_merges", "n_nodes", "n_classes", "compact", "max_token_len", "node_bytes", "smem_nodes", "reserved")]
+        "n_merges", "n_nodes", "n_classes", "compact", "max_token_len", "node_bytes", "smem_nodes", "pair_slots")]
 
 
 _lib = None
@@ -49,6 +49,7 @@ def _declare(L):
         "ecgb_vocab_create": ([vp, vp, vp, u32, i32, pp], i32),
         "ecgb_vocab_destroy": ([vp], i32),
         "ecgb_vocab_info": ([vp, C.POINTER(VocabInfo)], i32),
+        "ecgb_pairtab_host": ([vp, vp, vp, u32, vp, vp, u32, C.POINTER(u32), vp, vp], i32),
         "ecgb_encode_symbols": ([vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
         "ecgb_encode_batch": ([vp, vp, vp, sz, sz, vp, sz, vp, vp], i32),
         "ecgb_encode_text_host": ([vp, vp, sz, vp, sz, C.POINTER(sz)], i32),

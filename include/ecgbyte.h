@@ -101,10 +101,19 @@ typedef struct {
     uint32_t compact;       /* 1: 8-byte bitmap nodes (<= 31 classes), 0: wide nodes */
     uint32_t max_token_len; /* longest expanded sequence */
     uint32_t node_bytes;    /* size of the device node table */
-    uint32_t smem_nodes;    /* nodes the encode kernel keeps in shared memory */
-    uint32_t reserved;
+    uint32_t smem_nodes;    /* nodes the bitmap-trie kernels keep in shared memory */
+    uint32_t pair_slots;    /* slots of the two-symbol-stride table the fused encoder walks (0: none) */
 } ecgb_vocab_info_t;
 int ecgb_vocab_info(const ecgb_vocab *v, ecgb_vocab_info_t *out);
+
+/* Host-only view of the flattened trie the fused encoder walks (inspection and tests; no device
+ * needed): the two-symbol-stride "pair table" of the same merges (lib.rs:153-161 trie, states =
+ * nodes at even depth; layout documented in csrc/trie_host.h).  Two-call sizing through *n_ent_out
+ * (h_ent / h_tok may be NULL).  meta = {root_base, dead_base, W, NC, SM, SE, states, slots used};
+ * h_cls_out[b] = class of byte b (255: none). */
+int ecgb_pairtab_host(const uint32_t *h_seq, const uint64_t *h_seq_off, const uint32_t *h_ids,
+                      uint32_t n_merges, uint32_t *h_ent, uint16_t *h_tok, uint32_t cap,
+                      uint32_t *n_ent_out, uint32_t meta[8], uint8_t h_cls_out[256]);
 
 /* ------------------------------------------------------------------------- */
 /* E2  encode_text  (lib.rs:149-193) -- greedy longest match over the trie    */
