@@ -46,7 +46,8 @@ constexpr int kTPB = 256;                // threads per block of the merge kerne
 constexpr int kIPT = 16;                 // tokens per thread
 constexpr int kTile = kTPB * kIPT;
 constexpr int kBoundaryWords = 16;       // u32 words of boundary info per rank
-constexpr int kArgmaxBlocks = 592;       // 148 SMs x 4
+constexpr int kCtasPerSm = 4;            // co-resident CTAs per SM of the persistent kernels (launch bounds)
+constexpr int kMaxWorld = 16;            // ranks of one sharded run (the GPUs of one box)
 constexpr uint32_t kRedundantArgmax = 2048;  // candidate lists up to this size are scanned by every CTA
 constexpr int kChunkTiles = 3;           // resident tail: each CTA keeps up to 3 tiles of the stream in shared memory
 constexpr int kChunkCap = kChunkTiles * kTile;
@@ -61,6 +62,19 @@ struct PairTable {
     // (inbits marks listed slots).  NULL for tables that are never arg-maxed.
     const unsigned long long *tau;
     uint32_t *cand, *ncand, *inbits;
+    // persistent sharded loop: every add to this view of the table is also appended to the rank's
+    // outgoing patch list in the peers' memory (NULL otherwise)
+    struct PeerPush *push;
+};
+
+// Outgoing patch list of one merge step (persistent sharded loop): entry i goes to slot i of this
+// rank's inbox on every peer, written there directly over NVLink.
+struct PeerPush {
+    uint32_t *out_count;       // (local) entries appended so far in this step
+    uint32_t *overflow;        // (local) set when the inbox capacity is exceeded
+    uint32_t cap;
+    int rank, world;
+    uint2 *dst[kMaxWorld];     // dst[r]: this rank's inbox (for this step's parity) in rank r's memory
 };
 
 struct Best {
@@ -101,18 +115,48 @@ struct TrainView {
     DevState *dev;
     PairTable main, delta;
     Best *best;               // [max_merges + 1]
-    Best *partial;            // [kArgmaxBlocks]
+    Best *partial;            // [cta_stride + 1]
     uint32_t *tickets;        // [max_merges + 1] tile tickets, zero-initialised
     unsigned long long *tile_status;  // [max tiles] decoupled look-back (merge_kernel)
     Boundary *boundary;       // this rank's boundary info (device)
     unsigned long long *n_hist;  // [max_merges + 2] stream length before each step
     unsigned int *arrive;     // train_loop_kernel: CTAs that have finished the argmax of a step, cumulative
-    Boundary *cta_bd;         // [2][kArgmaxBlocks] resident tail: boundary record of every CTA's chunk, by step parity
-    uint32_t *cta_counts;     // [kArgmaxBlocks] resident tail: chunk lengths for the final write-back
+    Boundary *cta_bd;         // [2][cta_stride] resident tail: boundary record of every CTA's chunk, by step parity
+    uint32_t *cta_counts;     // [cta_stride] resident tail: chunk lengths for the final write-back
     uint32_t resident_ok;     // resident tail enabled
     uint32_t redundant_max;   // train_loop_kernel: candidate lists up to this size are scanned by every CTA
+    uint32_t cta_stride;      // CTA slots of partial / cta_bd / cta_counts (= SMs x kCtasPerSm)
+    unsigned int *gbar;       // persistent sharded loop: arrival counter of its grid barrier (cumulative)
+    unsigned int *abort;      // persistent sharded loop: set when a wait timed out; every spin loop gives up
     int rank, world;
 };
+
+// ---- device-initiated exchange of the persistent sharded loop (dist_loop_kernel) ----
+// Every rank owns a receive AREA in its own memory; peers map it (CUDA IPC between the one-process-per-GPU
+// ranks, or plain pointers inside one process) and write into it directly:
+//   hdr[parity][src]  64 B   flag  = step + 1 once src's patch list and next boundary record for that step are complete,
+//                            count = entries of that list, flag2 = step + 1 once the (x,x) run fields of src's record are in
+//   bd [parity][src]  64 B   Boundary record of src's shard for the stream a step of that parity reads
+//   ent[parity][src][cap]    (key, delta) histogram patches of src's merge pass
+// Two parities: a rank can be at most one step ahead of the slowest peer (it waits for every peer's flag of step t
+// before its argmax of step t + 1).
+struct PeerHdr { uint32_t flag, count, flag2, pad[13]; };
+static_assert(sizeof(PeerHdr) == 64, "header layout");
+struct PeerView {
+    int rank, world;
+    uint32_t cap;                  // list entries per (parity, source)
+    uint8_t *area[kMaxWorld];      // area[r] = rank r's area as mapped here; area[rank] is this rank's own
+    uint32_t *out_count;           // (local) [2] entries of this rank's outgoing list, by step parity
+    uint32_t *done_ctas;           // (local) CTAs that have flushed their patches, cumulative over steps
+    uint32_t *overflow;            // (local) outgoing list overflow
+    unsigned long long timeout_ns; // a wait for a peer gives up after this long (sets *abort)
+};
+__host__ __device__ inline size_t peer_hdr_off(int world, int parity, int src) { return ((size_t)parity * world + src) * 64; }
+__host__ __device__ inline size_t peer_bd_off(int world, int parity, int src) { return ((size_t)(2 + parity) * world + src) * 64; }
+__host__ __device__ inline size_t peer_ent_off(int world, uint32_t cap, int parity, int src) {
+    return (size_t)4 * world * 64 + ((size_t)parity * world + src) * (size_t)cap * 8;
+}
+__host__ __device__ inline size_t peer_area_bytes(int world, uint32_t cap) { return peer_ent_off(world, cap, 2, 0); }
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k) {
     k ^= k >> 16;
@@ -125,7 +169,22 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t k) {
 
 // tau_val: the candidate threshold (*t.tau), read by the caller once -- it only changes between passes,
 // and loading it here would put one more L2 round trip behind every atomic
+__device__ __forceinline__ void push_entry(const PeerPush &p, uint32_t key, int delta) {
+    // one atomic per converged group of callers
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(p.out_count, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t idx = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    if (idx >= p.cap) { *p.overflow = 1u; return; }
+    const uint2 e = make_uint2(key, (uint32_t)delta);
+    for (int r = 0; r < p.world; r++)
+        if (r != p.rank) p.dst[r][idx] = e;
+}
+
 __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta, unsigned long long tau_val) {
+    if (t.push != nullptr) push_entry(*t.push, key, (int)delta);
     uint32_t slot = hash_key(key) & t.mask;
     for (uint32_t probes = 0; probes <= t.mask; probes++) {
         uint32_t k = t.keys[slot];
@@ -154,6 +213,10 @@ constexpr int kPatchSlots = 1 << kPatchBits;
 struct PatchTable {
     uint32_t keys[kPatchSlots];
     int vals[kPatchSlots];
+    // persistent kernels: the global table may only change once every CTA has taken this step's argmax
+    // from it (gate counter >= gate_target); NULL when launches order the two
+    unsigned int *gate;
+    unsigned int gate_target;
 };
 
 __device__ __forceinline__ void table_add(const PairTable &t, uint32_t key, long long delta) {
@@ -175,7 +238,13 @@ __device__ __forceinline__ void patch_add(PatchTable &p, const PairTable &t, uin
         }
         slot = (slot + 1) & (kPatchSlots - 1);
     }
-    table_add(t, key, (long long)delta);  // private table crowded: go to the global one
+    // private table crowded: go to the global one
+    if (p.gate != nullptr) {
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int *>(p.gate) < p.gate_target)
+            if (++spins > (1u << 28)) break;
+    }
+    table_add(t, key, (long long)delta);
 }
 
 __device__ __forceinline__ void patch_clear(PatchTable &p) {
@@ -425,6 +494,8 @@ struct MergeSmem {
     int chunk_n;               // resident tail: tokens of this CTA's chunk
     uint32_t carry_ctx[2];     // resident tail: last two input tokens of the previous tile
     Boundary bd_near[5];       // resident tail: records of chunks blockIdx-2 .. blockIdx+2
+    Boundary bd_peer[kMaxWorld];  // persistent sharded loop: every rank's shard record for this step
+    PeerPush push;             // persistent sharded loop: where this step's patches go
     // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
     // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
@@ -477,10 +548,29 @@ __device__ __forceinline__ uint32_t stage_index(uint32_t x) { return x ^ ((x >> 
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
 // TICKETS: tiles are handed out by an atomic counter (any grid size); otherwise tile =
 // blockIdx + k * gridDim, which needs every block to be co-resident (cooperative launch).
+// a wait for a word in this rank's area that a peer writes over NVLink: true once *p == want, false when the
+// wait was abandoned (timeout or another wait already gave up)
+__device__ __forceinline__ bool wait_peer_word(const uint32_t *p, uint32_t want, volatile unsigned int *abort,
+                                               unsigned long long timeout_ns) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; spins++) {
+        uint32_t got;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p) : "memory");
+        if (got == want) return true;
+        if ((spins & 255u) == 255u) {
+            if (*abort) return false;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) { *abort = 1u; return false; }
+        }
+    }
+}
+
 template <bool TICKETS, bool RESIDENT>
 __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
                                            const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm,
-                                           uint16_t *chunk) {
+                                           uint16_t *chunk, const PeerView *pv = nullptr) {
     // Resident tail (chunk != nullptr, cooperative kernel only): the stream lives in the CTAs' shared
     // memory, one contiguous chunk each, and is merged in place; the chunks are shards exactly like the
     // ranks of a sharded run (all_bd = every CTA's boundary record), so no output offsets are needed.
@@ -497,6 +587,29 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     ECGB_MARK_DECL;
     __syncthreads();
     if (threadIdx.x == 32) sm.tau_val = upd.tau != nullptr ? *upd.tau : ~0ull;
+    const bool sharded = pv != nullptr && pv->world > 1;  // persistent sharded loop: the peers' shard records live in this rank's area
+    if (sharded) {
+        const int par = (int)(step & 1u);
+        const uint8_t *mine = pv->area[pv->rank];
+        if (same) {  // the run fields of the peers' records arrive in this step's second exchange
+            if (threadIdx.x < (unsigned)pv->world && (int)threadIdx.x != pv->rank)
+                wait_peer_word(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv->world, par, (int)threadIdx.x))->flag2,
+                               step + 1u, v.abort, pv->timeout_ns);
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < pv->world * kBoundaryWords; i += kTPB)
+            reinterpret_cast<uint32_t *>(sm.bd_peer)[i] = __ldcg(reinterpret_cast<const uint32_t *>(mine + peer_bd_off(pv->world, par, 0)) + i);
+        if (threadIdx.x == 0) {  // this step's patches: local table + every peer's inbox
+            PeerPush &pp = sm.push;
+            pp.out_count = pv->out_count + par;
+            pp.overflow = pv->overflow;
+            pp.cap = pv->cap;
+            pp.rank = pv->rank;
+            pp.world = pv->world;
+            for (int r = 0; r < pv->world; r++)
+                pp.dst[r] = reinterpret_cast<uint2 *>(pv->area[r] + peer_ent_off(pv->world, pv->cap, par, pv->rank));
+        }
+    }
     if (resident) {
         // the neighbours' records in one round trip; make_halo rarely needs anything further away
         const int me = (int)blockIdx.x;
@@ -507,16 +620,33 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 reinterpret_cast<uint32_t *>(&sm.bd_near[q])[wd] = reinterpret_cast<const uint32_t *>(&all_bd[r])[wd];
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-            sm.halo = make_halo_from(
-                [&](int r) -> const Boundary & { return (r >= me - 2 && r <= me + 2) ? sm.bd_near[r - me + 2] : all_bd[r]; },
-                true, me, (int)gridDim.x, a, b);
+        if (threadIdx.x == 0) {
+            auto local = [&](int r) -> const Boundary & { return (r >= me - 2 && r <= me + 2) ? sm.bd_near[r - me + 2] : all_bd[r]; };
+            if (sharded) {
+                // one chain of shards: the ranks before this one (one record each), this rank's chunks, the ranks after
+                const int rk = pv->rank, G = (int)gridDim.x;
+                sm.halo = make_halo_from(
+                    [&](int i) -> const Boundary & { return i < rk ? sm.bd_peer[i] : (i < rk + G ? local(i - rk) : sm.bd_peer[i - G + 1]); },
+                    true, rk + me, pv->world - 1 + G, a, b);
+            } else {
+                sm.halo = make_halo_from(local, true, me, (int)gridDim.x, a, b);
+            }
+        }
+    } else if (sharded) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm.halo = make_halo(sm.bd_peer, pv->rank, pv->world, a, b);
     } else if (threadIdx.x == 0) {
         sm.halo = make_halo(all_bd, v.rank, v.world, a, b);
     }
     patch_clear(sm.patch);
+    if (threadIdx.x == 0) {
+        sm.patch.gate = TICKETS ? nullptr : v.arrive;
+        sm.patch.gate_target = (step + 1u) * gridDim.x;
+    }
     __syncthreads();
     ECGB_MARK(1);
+    PairTable updp = upd;  // the view of the table the patches go through
+    if (sharded) updp.push = &sm.push;
     const Halo h = sm.halo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *const stage16 = reinterpret_cast<uint16_t *>(sm.out);
@@ -647,7 +777,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             int ns = __popc(site);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-            if (lane == 0) patch_add(sm.patch, upd, mk(a, b), -ns);  // the pair itself, per warp
+            if (lane == 0) patch_add(sm.patch, updp, mk(a, b), -ns);  // the pair itself, per warp
             const uint16_t *ctx = &sm.in[6 + threadIdx.x * kIPT];  // ctx[2 + i] = token at base + i
             uint32_t rem = site;
             while (rem) {
@@ -656,12 +786,12 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                 const uint32_t tm2 = ctx[i], tm1 = ctx[1 + i], tp2 = ctx[4 + i], tp3 = ctx[5 + i];
                 if (tm1 != kSentinel) {  // there is a left neighbour
                     const bool prev_site = tm2 == a && tm1 == b;  // site at p-2 (parity is implied)
-                    patch_add(sm.patch, upd, mk(tm1, a), -1);
-                    patch_add(sm.patch, upd, mk(prev_site ? z : tm1, z), +1);
+                    patch_add(sm.patch, updp, mk(tm1, a), -1);
+                    patch_add(sm.patch, updp, mk(prev_site ? z : tm1, z), +1);
                 }
                 if (tp2 != kSentinel && !(tp2 == a && tp3 == b)) {  // right neighbour that starts no site
-                    patch_add(sm.patch, upd, mk(b, tp2), -1);
-                    patch_add(sm.patch, upd, mk(z, tp2), +1);
+                    patch_add(sm.patch, updp, mk(b, tp2), -1);
+                    patch_add(sm.patch, updp, mk(z, tp2), +1);
                 }
             }
         }
@@ -711,6 +841,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             if (tile > 0) {
                 if (lane == 0) atomicExch(&v.tile_status[tile], pack_status(1, step, (unsigned long long)tile_total));
                 long long j = tile - 1;  // lane l looks at tile j - l
+                unsigned int lb_spins = 0;
                 for (;;) {
                     const long long idx = j - lane;
                     uint32_t flag = 2;            // tiles before the first one: an inclusive prefix of 0
@@ -740,6 +871,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
                         j -= 32;
                     }
                     // else: a needed tile is not published yet -> probe again
+                    if ((++lb_spins & 1023u) == 0 && v.abort != nullptr && *reinterpret_cast<volatile unsigned int *>(v.abort)) break;
                 }
             }
             if (lane == 0) {
@@ -778,7 +910,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         __syncthreads();  // the chunk is complete
         // record for the next step (other parity: slower CTAs may still be reading this step's records);
         // an (x,x) step adds the run information and a grid barrier of its own
-        if (warp == 0) chunk_boundary(chunk, (int)chunk_fill, kSentinel, false, &v.cta_bd[((step + 1) & 1) * kArgmaxBlocks + blockIdx.x]);
+        if (warp == 0) chunk_boundary(chunk, (int)chunk_fill, kSentinel, false, &v.cta_bd[((step + 1) & 1) * v.cta_stride + blockIdx.x]);
         if (threadIdx.x == 0) {
             sm.chunk_n = (int)chunk_fill;
             if (chunk_fill) atomicAdd(&v.n_hist[step + 1], chunk_fill);  // stream length after this step (zero-initialised)
@@ -789,11 +921,14 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         // short candidate lists on their own, without a grid barrier): cumulative arrival counter
         if (threadIdx.x == 0) {
             const unsigned int target = (step + 1u) * gridDim.x;
-            while (*reinterpret_cast<volatile unsigned int *>(v.arrive) < target) { }
+            unsigned int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int *>(v.arrive) < target) {
+                if ((++spins & 1023u) == 0 && *reinterpret_cast<volatile unsigned int *>(v.abort)) break;
+            }
         }
     }
     __syncthreads();
-    patch_flush(sm.patch, upd, sm.tau_val);
+    patch_flush(sm.patch, updp, sm.tau_val);
     ECGB_MARK(9);
 }
 
@@ -811,7 +946,32 @@ __global__ void __launch_bounds__(kTPB) merge_kernel(TrainView v, uint32_t step,
 // kernel: per step, a grid-wide argmax over the pair table, a grid barrier, the streaming
 // merge pass, a grid barrier.  No launches and no host round trips inside the loop.
 // grid-wide fold of per-block partial maxima; every block ends up with the same result
-__device__ __forceinline__ Best grid_best(cg::grid_group &grid, const TrainView &v, Best mine, Best *s_best) {
+// Grid barrier of the persistent sharded loop: cumulative arrival counter, and -- unlike cg::grid_group::sync --
+// a way out: every spin loop of that kernel also watches *abort, which a timed-out wait for a peer sets, so a
+// rank whose peer died ends with an error instead of hanging the GPU.
+struct AbortableGrid {
+    unsigned int *ctr;
+    volatile unsigned int *abort;
+    unsigned int gen;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        gen++;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            const unsigned int target = gen * gridDim.x;
+            unsigned int spins = 0;
+            while ((int)(*reinterpret_cast<volatile unsigned int *>(ctr) - target) < 0) {
+                if ((++spins & 255u) == 0 && *abort) break;
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
+template <class Grid>
+__device__ __forceinline__ Best grid_best(Grid &grid, const TrainView &v, Best mine, Best *s_best) {
     Best bb = block_best(mine);
     if (threadIdx.x == 0) v.partial[blockIdx.x] = bb;
     grid.sync();
@@ -827,7 +987,8 @@ __device__ __forceinline__ Best grid_best(cg::grid_group &grid, const TrainView 
 }
 
 // argmax (lib.rs:92-94) for a cooperative grid; every thread returns the same winner.
-__device__ __forceinline__ Best grid_argmax(cg::grid_group &grid, const TrainView &v, Best *s_best_p) {
+template <class Grid>
+__device__ __forceinline__ Best grid_argmax(Grid &grid, const TrainView &v, Best *s_best_p) {
     Best &s_best = *s_best_p;
     const PairTable &t = v.main;
     const uint64_t cap = (uint64_t)t.mask + 1;
@@ -862,10 +1023,10 @@ __device__ __forceinline__ Best grid_argmax(cg::grid_group &grid, const TrainVie
                 if (c != 0) mine = better(mine, Best{c, t.keys[slot], 1});
             }
             const Best b0 = block_best(mine);
-            if (threadIdx.x == 0) v.partial[kArgmaxBlocks] = b0;
+            if (threadIdx.x == 0) v.partial[v.cta_stride] = b0;
         }
         grid.sync();
-        fin = v.partial[kArgmaxBlocks];
+        fin = v.partial[v.cta_stride];
     } else {
         for (uint64_t i = gtid; i < nc; i += gthreads) {
             const uint32_t slot = t.cand[i];
@@ -899,7 +1060,34 @@ __device__ __forceinline__ Best grid_argmax(cg::grid_group &grid, const TrainVie
     return fin;
 }
 
-__global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32_t n_steps) {
+// Resident tail, end of the run: back to one contiguous stream in tok[step & 1] (step = merges done),
+// where the host expects it.
+template <class Grid>
+__device__ __forceinline__ void resident_write_back(Grid &grid, const TrainView &v, uint32_t step, int cn, const uint16_t *chunk) {
+    if (threadIdx.x == 0) v.cta_counts[blockIdx.x] = (uint32_t)cn;
+    grid.sync();
+    unsigned long long pre = 0, all = 0;
+    for (uint32_t j = threadIdx.x; j < gridDim.x; j += kTPB) {
+        const unsigned long long c = __ldcg(&v.cta_counts[j]);
+        all += c;
+        if (j < blockIdx.x) pre += c;
+    }
+    __shared__ unsigned long long s_pre[kTPB / 32], s_all[kTPB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pre += __shfl_xor_sync(0xffffffffu, pre, o);
+        all += __shfl_xor_sync(0xffffffffu, all, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_pre[threadIdx.x >> 5] = pre; s_all[threadIdx.x >> 5] = all; }
+    __syncthreads();
+    pre = all = 0;
+    for (int q = 0; q < kTPB / 32; q++) { pre += s_pre[q]; all += s_all[q]; }
+    uint16_t *dst = v.tok[step & 1] + pre;
+    for (int i = threadIdx.x; i < cn; i += kTPB) dst[i] = chunk[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) v.dev->n[step & 1] = all;
+}
+
+__global__ void __launch_bounds__(kTPB, kCtasPerSm) train_loop_kernel(TrainView v, uint32_t n_steps) {
     cg::grid_group grid = cg::this_grid();
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
@@ -938,47 +1126,228 @@ __global__ void __launch_bounds__(kTPB, 4) train_loop_kernel(TrainView v, uint32
         if (res_mode) {
             const bool xx = (fin.key >> 16) == (fin.key & 0xFFFFu);
             if (xx || res_fresh) {  // otherwise the records published by the previous pass are all that is needed
-                if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, xx, &v.cta_bd[(step & 1) * kArgmaxBlocks + blockIdx.x]);
+                if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, xx, &v.cta_bd[(step & 1) * v.cta_stride + blockIdx.x]);
                 grid.sync();  // every chunk's boundary record is visible
             }
             res_fresh = false;
         }
-        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (step & 1) * kArgmaxBlocks, v.main, sm, chunk);
+        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (step & 1) * v.cta_stride, v.main, sm, chunk);
         else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr);
         ECGB_MARK_RESET;
         grid.sync();
         ECGB_MARK(10);
     }
-    if (res_mode) {
-        // back to one contiguous stream in tok[step & 1] (step = merges done), where the host expects it
-        const int cn = sm.chunk_n;
-        if (threadIdx.x == 0) v.cta_counts[blockIdx.x] = (uint32_t)cn;
-        grid.sync();
-        unsigned long long pre = 0, all = 0;
-        for (uint32_t j = threadIdx.x; j < gridDim.x; j += kTPB) {
-            const unsigned long long c = __ldcg(&v.cta_counts[j]);
-            all += c;
-            if (j < blockIdx.x) pre += c;
+    if (res_mode) resident_write_back(grid, v, step, sm.chunk_n, chunk);
+}
+
+// ------------------------------------------------------------------ persistent sharded loop
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t val) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(val) : "memory");
+}
+
+// Record of this rank's shard as the stream that step s reads, without the (x,x) run fields.  One thread;
+// everything it reads was written by other CTAs of this grid before they arrived at the counter the caller
+// has just observed.
+__device__ void shard_record(const TrainView &v, uint32_t s, bool resident, Boundary *out) {
+    Boundary bd;
+    memset(&bd, 0, sizeof(bd));
+    for (int i = 0; i < 3; i++) bd.first[i] = kSentinel;
+    bd.last[0] = bd.last[1] = kSentinel;
+    if (!resident) {
+        const volatile uint16_t *tok = v.tok[s & 1];
+        const unsigned long long n = *reinterpret_cast<const volatile unsigned long long *>(&v.dev->n[s & 1]);
+        bd.n_lo = (uint32_t)n;
+        bd.n_hi = (uint32_t)(n >> 32);
+        for (int i = 0; i < 3 && (unsigned long long)i < n; i++) bd.first[i] = tok[i];
+        if (n >= 1) bd.last[1] = tok[n - 1];
+        if (n >= 2) bd.last[0] = tok[n - 2];
+    } else {
+        const Boundary *cb = v.cta_bd + (size_t)(s & 1) * v.cta_stride;
+        const unsigned long long n = *reinterpret_cast<const volatile unsigned long long *>(&v.n_hist[s]);  // sum of the chunk lengths
+        bd.n_lo = (uint32_t)n;
+        bd.n_hi = (uint32_t)(n >> 32);
+        int nf = 0;
+        for (int c = 0; c < (int)gridDim.x && nf < 3; c++) {
+            const uint32_t nc = ld_vol(&cb[c].n_lo);
+            for (int i = 0; i < 3 && (uint32_t)i < nc && nf < 3; i++) bd.first[nf++] = ld_vol(&cb[c].first[i]);
         }
-        __shared__ unsigned long long s_pre[kTPB / 32], s_all[kTPB / 32];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            pre += __shfl_xor_sync(0xffffffffu, pre, o);
-            all += __shfl_xor_sync(0xffffffffu, all, o);
+        uint32_t got[2];
+        int ng = 0;
+        for (int c = (int)gridDim.x - 1; c >= 0 && ng < 2; c--) {
+            const uint32_t nc = ld_vol(&cb[c].n_lo);
+            if (nc >= 1) got[ng++] = ld_vol(&cb[c].last[1]);
+            if (nc >= 2 && ng < 2) got[ng++] = ld_vol(&cb[c].last[0]);
         }
-        if ((threadIdx.x & 31) == 0) { s_pre[threadIdx.x >> 5] = pre; s_all[threadIdx.x >> 5] = all; }
-        __syncthreads();
-        pre = all = 0;
-        for (int q = 0; q < kTPB / 32; q++) { pre += s_pre[q]; all += s_all[q]; }
-        uint16_t *dst = v.tok[step & 1] + pre;
-        for (int i = threadIdx.x; i < cn; i += kTPB) dst[i] = chunk[i];
-        if (blockIdx.x == 0 && threadIdx.x == 0) v.dev->n[step & 1] = all;
+        if (ng >= 1) bd.last[1] = got[0];
+        if (ng >= 2) bd.last[0] = got[1];
     }
+    *out = bd;
+}
+
+// The (x,x) run fields of this rank's record for the pair (a, a): parity of the run of a that ends the shard
+// and whether the shard is nothing else.  Warp 0 of one CTA; valid in lane 0.
+__device__ void shard_run_fields(const TrainView &v, uint32_t s, bool resident, uint32_t a, uint32_t *trail_par, uint32_t *all_a) {
+    const int lane = threadIdx.x & 31;
+    if (resident) {  // fold the chunks' fields from the end of the shard
+        if (lane == 0) {
+            const Boundary *cb = v.cta_bd + (size_t)(s & 1) * v.cta_stride;
+            uint32_t par = 0;
+            bool all = true;
+            for (int c = (int)gridDim.x - 1; c >= 0; c--) {
+                const uint32_t nc = ld_vol(&cb[c].n_lo);
+                if (nc == 0) continue;
+                if (ld_vol(&cb[c].all_a)) { par ^= nc & 1u; continue; }
+                par ^= ld_vol(&cb[c].trail_par);
+                all = false;
+                break;
+            }
+            *trail_par = par;
+            *all_a = all ? 1u : 0u;
+        }
+        return;
+    }
+    const uint16_t *tok = v.tok[s & 1];
+    const long long n = (long long)v.dev->n[s & 1];
+    bool hit = false;
+    long long found = -1;
+    for (long long p = n - 1; p >= 0 && !hit; p -= 32) {
+        const long long q = p - lane;
+        const bool nonx = q >= 0 && tok[q] != a;
+        const unsigned m = __ballot_sync(0xffffffffu, nonx);
+        if (m) { found = p - (__ffs(m) - 1); hit = true; }
+    }
+    const long long run = n - 1 - found;
+    *trail_par = (uint32_t)(run & 1);
+    *all_a = run == n ? 1u : 0u;
+}
+
+// byte_pair_encoding (lib.rs:85-117) over a corpus cut into contiguous shards, one persistent cooperative
+// kernel per rank (GPU), all running at the same time.  Per merge step a rank takes the argmax from ITS copy
+// of the global pair histogram (the copies are identical, so is the winner), merges the pair in its shard
+// -- the halo across shard borders comes from the peers' 64-byte shard records -- and writes its histogram
+// patches both into its own table and, entry by entry over NVLink, into its inbox on every peer; the last CTA
+// to finish publishes the shard record of the next stream and raises the step's flag on the peers.  Then
+// every rank applies the patches the peers left in its area.  One exchange per step ((x,x) steps add one
+// for the run parities), no launches, no host, no collective library inside the loop.
+__global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_loop_kernel(TrainView v, PeerView pv, uint32_t n_steps) {
+    __shared__ MergeSmem sm;
+    __shared__ Best s_best;
+    __shared__ int s_last;
+    extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
+    AbortableGrid grid{v.gbar, v.abort, 0u};
+    volatile unsigned int *abort = v.abort;
+    bool res_mode = false, res_fresh = false;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    uint8_t *const mine = pv.area[pv.rank];
+    uint32_t step = 0;
+    for (; step < n_steps; step++) {
+        if (*abort) break;
+        if (!res_mode && v.resident_ok) {
+            // the shard now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
+            const unsigned long long n = v.dev->n[step & 1];
+            const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;
+            if (clen <= (unsigned long long)kChunkCap) {
+                const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
+                const unsigned long long hi = min(n, lo + clen);
+                const uint16_t *src = v.tok[step & 1] + lo;
+                const int cn = (int)(hi - lo);
+                for (int i = threadIdx.x * 8; i + 8 <= cn; i += kTPB * 8)
+                    *reinterpret_cast<uint4 *>(chunk + i) = *reinterpret_cast<const uint4 *>(src + i);
+                for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk[i] = src[i];
+                if (threadIdx.x == 0) sm.chunk_n = cn;
+                res_mode = res_fresh = true;
+                __syncthreads();
+            }
+        }
+        const Best fin = grid_argmax(grid, v, &s_best);
+        if (gtid == 0) {
+            v.best[step] = fin;
+            if (fin.count == 0) atomicMin(&v.dev->done_step, step);
+        }
+        if (fin.count == 0) break;  // no pair left (lib.rs:88-90); the same on every rank
+        if (threadIdx.x == 0) atomicAdd(v.arrive, 1u);
+        const int par = (int)(step & 1u);
+        const uint32_t a = fin.key >> 16;
+        const bool xx = a == (fin.key & 0xFFFFu);
+        if (res_mode && (xx || res_fresh)) {
+            if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, a, xx, &v.cta_bd[(size_t)par * v.cta_stride + blockIdx.x]);
+            grid.sync();
+        }
+        res_fresh = false;
+        if (xx && blockIdx.x == 0 && threadIdx.x < 32) {
+            // second exchange of an (x,x) step: the run fields of this shard's record
+            uint32_t tp = 0, alla = 0;
+            shard_run_fields(v, step, res_mode, a, &tp, &alla);
+            if (threadIdx.x == 0) {
+                for (int r = 0; r < pv.world; r++) {
+                    Boundary *dst = reinterpret_cast<Boundary *>(pv.area[r] + peer_bd_off(pv.world, par, pv.rank));
+                    dst->trail_par = tp;
+                    dst->all_a = alla;
+                }
+                __threadfence_system();
+                for (int r = 0; r < pv.world; r++)
+                    if (r != pv.rank)
+                        st_release_sys(&reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->flag2, step + 1u);
+            }
+        }
+        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (size_t)par * v.cta_stride, v.main, sm, chunk, &pv);
+        else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr, &pv);
+        // this CTA's patches are in the local table and on their way to the peers
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int old = atomicAdd(pv.done_ctas, 1u);
+            s_last = old == (step + 1u) * gridDim.x - 1u;
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            // the whole rank has finished the pass: shard record of the next stream, list length, flag
+            __threadfence();
+            Boundary bd;
+            shard_record(v, step + 1u, res_mode, &bd);
+            uint32_t cnt = ld_vol(pv.out_count + par);
+            if (cnt > pv.cap) cnt = pv.cap;  // overflow was flagged by push_entry
+            pv.out_count[par ^ 1] = 0u;     // nobody appends before the barrier that ends this step
+            for (int r = 0; r < pv.world; r++) {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(pv.area[r] + peer_bd_off(pv.world, par ^ 1, pv.rank));
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&bd);
+#pragma unroll
+                for (int w = 0; w < kBoundaryWords; w++) dst[w] = src[w];
+                if (r != pv.rank) reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->count = cnt;
+            }
+            __threadfence_system();
+            for (int r = 0; r < pv.world; r++)
+                if (r != pv.rank) st_release_sys(&reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->flag, step + 1u);
+        }
+        // the peers' patches of this step
+        if (threadIdx.x < (unsigned)pv.world && (int)threadIdx.x != pv.rank)
+            wait_peer_word(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv.world, par, (int)threadIdx.x))->flag, step + 1u, abort,
+                           pv.timeout_ns);
+        __syncthreads();
+        {
+            const unsigned long long tau_val = __ldcg(v.main.tau);
+            for (int r = 0; r < pv.world; r++) {
+                if (r == pv.rank) continue;
+                const uint32_t cnt = min(__ldcg(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv.world, par, r))->count), pv.cap);
+                const uint2 *ent = reinterpret_cast<const uint2 *>(mine + peer_ent_off(pv.world, pv.cap, par, r));
+                for (uint64_t i = gtid; i < cnt; i += gthreads) {
+                    const uint2 e = __ldcg(ent + i);
+                    table_add(v.main, e.x, (long long)(int)e.y, tau_val);
+                }
+            }
+        }
+        grid.sync();
+    }
+    if (res_mode) resident_write_back(grid, v, step, sm.chunk_n, chunk);
+    if (gtid == 0) v.dev->cur_step = step;
 }
 
 // Sharded training: the argmax of one step as a cooperative launch (candidate list instead of a full
 // table scan), then this shard's boundary record for the winning pair, as argmax_kernel leaves it.
-__global__ void __launch_bounds__(kTPB, 4) dist_argmax_kernel(TrainView v, uint32_t step) {
+__global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_argmax_kernel(TrainView v, uint32_t step) {
     cg::grid_group grid = cg::this_grid();
     __shared__ Best s_best;
     if (step == kStepFromDevice) step = v.dev->cur_step;
@@ -1081,6 +1450,12 @@ struct ecgb_trainer {
     uint32_t *d_list = nullptr;  // this rank's delta list
     int coop_grid = 0;           // grid of dist_argmax_kernel (all CTAs co-resident)
     bool device_steps = false;   // steps were issued with ECGB_STEP_DEVICE
+    // persistent sharded loop: this rank's receive area and its local counters
+    uint8_t *peer_area = nullptr;
+    uint64_t peer_bytes = 0;
+    int peer_world = 0;
+    uint32_t peer_cap = 0;
+    uint32_t *peer_ctr = nullptr;  // out_count[2], done_ctas, overflow
 };
 
 static int dev_alloc(ecgb_trainer *t, void **p, size_t bytes, bool zero) {
@@ -1105,6 +1480,7 @@ static int alloc_table(ecgb_trainer *t, PairTable *pt, uint32_t log2cap) {
     pt->mask = (uint32_t)(cap - 1);
     pt->tau = nullptr;
     pt->cand = pt->ncand = pt->inbits = nullptr;
+    pt->push = nullptr;
     cudaError_t e = cudaMemset(pt->keys, 0xFF, cap * 4);
     if (e != cudaSuccess) return fail(ECGB_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     return ECGB_OK;
@@ -1126,6 +1502,7 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
     t->capacity = capacity_tokens;
     t->max_merges = max_merges;
     t->list_cap = 1u << 15;
+    t->v.cta_stride = (uint32_t)(t->sms * kCtasPerSm);
     DeviceGuard g(device);
     const size_t tokbytes = (capacity_tokens + 64) * 2;
     const size_t ntiles = (size_t)(capacity_tokens / kTile) + 2;
@@ -1145,14 +1522,16 @@ extern "C" int ecgb_trainer_create(int device, uint64_t capacity_tokens, uint32_
         t->v.main.ncand = reinterpret_cast<uint32_t *>(tau + 1);
     }
     if (!rc) rc = dev_alloc(t, (void **)&t->v.best, sizeof(Best) * ((size_t)max_merges + 1), true);
-    if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * (kArgmaxBlocks + 1), true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.partial, sizeof(Best) * ((size_t)t->v.cta_stride + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tickets, 4 * ((size_t)max_merges + 1), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.tile_status, 8 * ntiles, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.boundary, sizeof(Boundary), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.n_hist, 8 * ((size_t)max_merges + 2), true);
     if (!rc) rc = dev_alloc(t, (void **)&t->v.arrive, 16, true);
-    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_bd, sizeof(Boundary) * 2 * kArgmaxBlocks, true);
-    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_counts, 4 * kArgmaxBlocks, true);
+    t->v.gbar = t->v.arrive + 1;
+    t->v.abort = t->v.arrive + 2;
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_bd, sizeof(Boundary) * 2 * (size_t)t->v.cta_stride, true);
+    if (!rc) rc = dev_alloc(t, (void **)&t->v.cta_counts, 4 * (size_t)t->v.cta_stride, true);
     if (!rc) rc = dev_alloc(t, (void **)&t->d_list, (size_t)(4 + 3 * (size_t)t->list_cap) * 4, true);
     if (rc) { ecgb_trainer_destroy(t); return rc; }
     t->v.rank = 0;
@@ -1240,6 +1619,14 @@ static int check_tables(ecgb_trainer *t) {
     uint32_t dflags[2] = {0, 0};
     ECGB_CUDA(cudaMemcpy(dflags, t->v.delta.used, 8, cudaMemcpyDeviceToHost));
     if (dflags[1]) return fail(ECGB_ECAPACITY, "delta table overflow");
+    uint32_t sync_words[3] = {0, 0, 0};  // arrive, gbar, abort
+    ECGB_CUDA(cudaMemcpy(sync_words, t->v.arrive, 12, cudaMemcpyDeviceToHost));
+    if (sync_words[2]) return fail(ECGB_ECUDA, "sharded training: a wait for a peer rank timed out (is every rank running?)");
+    if (t->peer_ctr) {
+        uint32_t ctr[4] = {0, 0, 0, 0};
+        ECGB_CUDA(cudaMemcpy(ctr, t->peer_ctr, 16, cudaMemcpyDeviceToHost));
+        if (ctr[3]) return fail(ECGB_ECAPACITY, "sharded training: a step produced more than %u histogram patches per rank", t->peer_cap);
+    }
     return ECGB_OK;
 }
 
@@ -1264,8 +1651,8 @@ extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *
     ECGB_CUDA(cudaFuncSetAttribute(train_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_loop_kernel, kTPB, dyn_smem));
     if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "train_loop_kernel does not fit on this device");
-    int grid = t->sms * std::min(per_sm, 4);
-    if (grid > kArgmaxBlocks) grid = kArgmaxBlocks;
+    int grid = t->sms * std::min(per_sm, kCtasPerSm);
+    if (grid > (int)t->v.cta_stride) grid = (int)t->v.cta_stride;
     if (num_merges > 0) {
         TrainView view = t->v;
         const char *knob = getenv("ECGB_REDUNDANT_ARGMAX");  // tuning knob (profiles/train_knobs.py)
@@ -1448,13 +1835,13 @@ extern "C" int ecgb_trainer_dist_commit(ecgb_trainer *t, uint32_t step, const vo
                                                t->list_cap, t->v.world);
     static const bool full_scan = getenv("ECGB_DIST_FULLSCAN") != nullptr;  // A/B knob: the old full-table argmax
     if (full_scan) {
-        argmax_kernel<<<kArgmaxBlocks, 256, 0, st>>>(t->v, step);
+        argmax_kernel<<<(int)t->v.cta_stride, 256, 0, st>>>(t->v, step);
     } else {
     if (t->coop_grid == 0) {
         int per_sm = 0;
         ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_argmax_kernel, kTPB, 0));
         if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "dist_argmax_kernel does not fit on this device");
-        t->coop_grid = std::min(t->sms * std::min(per_sm, 4), kArgmaxBlocks);
+        t->coop_grid = std::min(t->sms * std::min(per_sm, kCtasPerSm), (int)t->v.cta_stride);
     }
     {
         TrainView view = t->v;
@@ -1486,6 +1873,126 @@ extern "C" int ecgb_trainer_dist_merge(ecgb_trainer *t, uint32_t step, const voi
     ECGB_CUDA(cudaGetLastError());
     if (step == kStepFromDevice) t->device_steps = true;
     else t->steps_done = step + 1;
+    return ECGB_OK;
+}
+
+// ------------------------------------------------------------------ persistent sharded loop (device-initiated exchange)
+
+// Allocate (once) and clear this rank's receive area for a run over `world` ranks.  The peers need its address:
+// inside one process the pointer itself, between processes an IPC handle (ecgb_ipc_export / ecgb_ipc_open).
+// Clearing must be complete on EVERY rank before any rank calls ecgb_trainer_dist_run (host-side barrier).
+extern "C" int ecgb_trainer_peer_area(ecgb_trainer *t, int world, void **d_area, uint64_t *bytes) {
+    ECGB_REQUIRE(t && d_area && bytes, "NULL argument");
+    ECGB_REQUIRE(world >= 1 && world <= kMaxWorld, "world %d out of range [1, %d]", world, kMaxWorld);
+    DeviceGuard g(t->device);
+    const uint32_t cap = 1u << 20;  // patch entries per (parity, source): 8 MB each
+    const uint64_t need = peer_area_bytes(world, cap);
+    if (t->peer_area == nullptr || t->peer_world != world) {
+        ECGB_REQUIRE(t->peer_area == nullptr, "the receive area was created for %d ranks", t->peer_world);
+        int rc = dev_alloc(t, (void **)&t->peer_area, need, false);
+        if (!rc) rc = dev_alloc(t, (void **)&t->peer_ctr, 16, true);
+        if (rc) return rc;
+        t->peer_bytes = need;
+        t->peer_world = world;
+        t->peer_cap = cap;
+    }
+    // headers and records only: list entries are never read beyond the published count
+    ECGB_CUDA(cudaMemset(t->peer_area, 0, peer_ent_off(world, cap, 0, 0)));
+    ECGB_CUDA(cudaMemset(t->peer_ctr, 0, 16));
+    ECGB_CUDA(cudaDeviceSynchronize());
+    *d_area = t->peer_area;
+    *bytes = need;
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_ipc_export(const void *d_ptr, uint8_t handle[64]) {
+    ECGB_REQUIRE(d_ptr && handle, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ECGB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    std::memcpy(handle, &h, 64);
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_ipc_open(const uint8_t handle[64], int device, void **d_ptr) {
+    ECGB_REQUIRE(d_ptr && handle, "NULL argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    ECGB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ECGB_OK;
+}
+
+extern "C" int ecgb_ipc_close(void *d_ptr, int device) {
+    if (!d_ptr) return ECGB_OK;
+    DeviceGuard g(device);
+    ECGB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return ECGB_OK;
+}
+
+// Apply every rank's delta list to this rank's copy of the global histogram (the get_stats exchange that
+// precedes ecgb_trainer_dist_run; ecgb_trainer_dist_commit without the argmax).
+extern "C" int ecgb_trainer_dist_apply(ecgb_trainer *t, const void *d_all_lists, int world, void *stream) {
+    ECGB_REQUIRE(t && d_all_lists, "NULL argument");
+    ECGB_REQUIRE(world >= 1 && world <= kMaxWorld, "world %d out of range", world);
+    DeviceGuard g(t->device);
+    const uint32_t list_words = 4 + 3 * t->list_cap;
+    apply_lists_kernel<<<t->sms, 256, 0, as_stream(stream)>>>(t->v.main, static_cast<const uint32_t *>(d_all_lists), list_words,
+                                                              t->list_cap, world);
+    ECGB_CUDA(cudaGetLastError());
+    return ECGB_OK;
+}
+
+// Launch the persistent sharded loop of this rank (asynchronous; every rank of the run must launch, each on
+// its own device or -- with max_ctas small enough for all of them to be co-resident -- on one device).
+// d_areas[r] = rank r's receive area as addressable from this process; d_all_boundaries = the gathered
+// records of ecgb_trainer_dist_begin.  The table must hold the global histogram (dist_count + dist_apply).
+// Read the outcome with ecgb_trainer_results.
+extern "C" int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
+                                     uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream) {
+    ECGB_REQUIRE(t && d_areas && d_all_boundaries, "NULL argument");
+    ECGB_REQUIRE(t->loaded && t->steps_done == 0 && !t->device_steps, "load the shard first");
+    ECGB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+    ECGB_REQUIRE(t->peer_area != nullptr && t->peer_world == world, "call ecgb_trainer_peer_area(world) first");
+    ECGB_REQUIRE(d_areas[rank] == t->peer_area, "d_areas[rank] must be this trainer's own area");
+    ECGB_REQUIRE(num_merges <= t->max_merges, "num_merges %u > max_merges %u", num_merges, t->max_merges);
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    t->v.rank = rank;
+    t->v.world = world;
+    // the records of the initial stream (step 0 reads parity 0)
+    ECGB_CUDA(cudaMemcpyAsync(t->peer_area + peer_bd_off(world, 0, 0), d_all_boundaries, sizeof(Boundary) * (size_t)world,
+                              cudaMemcpyDeviceToDevice, st));
+    int per_sm = 0;
+    const size_t dyn_smem = (size_t)kChunkCap * sizeof(uint16_t);
+    ECGB_CUDA(cudaFuncSetAttribute(dist_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_loop_kernel, kTPB, dyn_smem));
+    if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "dist_loop_kernel does not fit on this device");
+    int grid = std::min(t->sms * std::min(per_sm, kCtasPerSm), (int)t->v.cta_stride);
+    if (max_ctas > 0) grid = std::min(grid, (int)max_ctas);
+    TrainView view = t->v;
+    view.redundant_max = kRedundantArgmax;
+    const char *knob = getenv("ECGB_RESIDENT_TAIL");
+    view.resident_ok = knob ? (uint32_t)atoi(knob) : 1u;
+    PeerView pv{};
+    pv.rank = rank;
+    pv.world = world;
+    pv.cap = t->peer_cap;
+    for (int r = 0; r < world; r++) {
+        ECGB_REQUIRE(d_areas[r] != nullptr, "d_areas[%d] is NULL", r);
+        pv.area[r] = static_cast<uint8_t *>(d_areas[r]);
+    }
+    pv.out_count = t->peer_ctr;
+    pv.done_ctas = t->peer_ctr + 2;
+    pv.overflow = t->peer_ctr + 3;
+    pv.timeout_ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 30.0) * 1e9);
+    uint32_t steps = num_merges;
+    void *kargs[] = {&view, &pv, &steps};
+    ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)dist_loop_kernel, dim3(grid), dim3(kTPB), kargs, dyn_smem, st));
+    ECGB_CUDA(cudaGetLastError());
+    t->device_steps = true;
     return ECGB_OK;
 }
 

@@ -457,6 +457,22 @@ class Trainer:
         """Increment the device-side step counter (see STEP_DEVICE)."""
         check(lib().ecgb_trainer_dist_advance(self._h, _stream(device)))
 
+    # ---- persistent sharded loop: device-initiated exchange over peer memory ----
+    def peer_area(self, world):
+        """Allocates / clears this rank's receive area -> (device pointer, bytes)."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        check(lib().ecgb_trainer_peer_area(self._h, int(world), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def dist_apply(self, all_lists, world):
+        check(lib().ecgb_trainer_dist_apply(self._h, _ptr(all_lists), int(world), _stream(all_lists.device)))
+
+    def dist_run(self, rank, world, areas, all_boundaries, num_merges, max_ctas=0, timeout_s=0.0):
+        """areas: device pointers (ints) of every rank's receive area as addressable here."""
+        arr = (C.c_void_p * int(world))(*[C.c_void_p(a) for a in areas])
+        check(lib().ecgb_trainer_dist_run(self._h, int(rank), int(world), arr, _ptr(all_boundaries), int(num_merges),
+                                          int(max_ctas), float(timeout_s), _stream(all_boundaries.device)))
+
     def results(self, n_steps):
         m = int(n_steps)
         pairs = np.zeros((max(m, 1), 2), np.uint32)

@@ -47,6 +47,14 @@ class TorchExchange:
     def all_gather(self, out, inp):
         self.dist.all_gather_into_tensor(out, inp, group=self.group)
 
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
 
 def _graph_default(default):
     v = os.environ.get("ECGB_DIST_GRAPH")
@@ -85,6 +93,112 @@ def train_shard(shard, num_merges, exchange=None, device=None, table_log2=0, che
         _run_steps(one_step, num_merges, dev, use_graph)
         pairs, counts, ntied = tr.results(num_merges)
     return pairs, counts, ntied, tr
+
+
+class ShardedTrainer:
+    """The persistent sharded loop (csrc/train.cu dist_loop_kernel), one process per GPU: ONE cooperative kernel
+    per rank runs every merge step and exchanges histogram patches and shard records with the peers by writing
+    straight into their memory over NVLink (CUDA IPC mappings of each rank's receive area).  torch.distributed is
+    used for the set-up only: IPC handles, the initial boundary records and get_stats lists, two barriers."""
+
+    def __init__(self, capacity_tokens, max_merges, exchange=None, device=None, table_log2=0):
+        import ctypes as C
+        from . import _lib
+        self.ex = exchange or TorchExchange()
+        self.tr = Trainer(max(int(capacity_tokens), 1), max_merges, device=device, table_log2=table_log2)
+        self.dev = torch.device("cuda", self.tr.device)
+        ex, tr = self.ex, self.tr
+        self.area, self.area_bytes = tr.peer_area(ex.world)
+        h = (C.c_ubyte * 64)()
+        _lib.check(_lib.lib().ecgb_ipc_export(C.c_void_p(self.area), h))
+        handles = ex.all_gather_object(bytes(h))
+        self.areas, self._opened = [], []
+        for r in range(ex.world):
+            if r == ex.rank:
+                self.areas.append(self.area)
+                continue
+            p = C.c_void_p()
+            _lib.check(_lib.lib().ecgb_ipc_open(handles[r], tr.device, C.byref(p)))
+            self.areas.append(p.value)
+            self._opened.append(p.value)
+        bbytes, lbytes = tr.dist_sizes()
+        self._bnd = torch.zeros(bbytes, dtype=torch.uint8, device=self.dev)
+        self._all_bnd = torch.zeros(bbytes * ex.world, dtype=torch.uint8, device=self.dev)
+        self._lst = torch.zeros(lbytes, dtype=torch.uint8, device=self.dev)
+        self._all_lst = torch.zeros(lbytes * ex.world, dtype=torch.uint8, device=self.dev)
+
+    def train(self, shard, num_merges, max_ctas=0, timeout_s=0.0):
+        """shard: this rank's contiguous piece of the corpus.  -> (pairs, counts, ntied), identical on every rank."""
+        ex, tr = self.ex, self.tr
+        tr.load(shard)
+        with torch.cuda.device(self.dev):
+            tr.peer_area(ex.world)  # clears headers and counters; the collectives below order it before any peer's run
+            tr.dist_begin(ex.rank, ex.world, self._bnd)
+            ex.all_gather(self._all_bnd, self._bnd)
+            tr.dist_count(self._all_bnd, self._lst)
+            ex.all_gather(self._all_lst, self._lst)
+            tr.dist_apply(self._all_lst, ex.world)
+            torch.cuda.synchronize(self.dev)
+            ex.barrier()
+            tr.dist_run(ex.rank, ex.world, self.areas, self._all_bnd, num_merges, max_ctas=max_ctas, timeout_s=timeout_s)
+            return tr.results(num_merges)
+
+    def close(self):
+        from . import _lib
+        import ctypes as C
+        for p in self._opened:
+            _lib.lib().ecgb_ipc_close(C.c_void_p(p), self.tr.device)
+        self._opened = []
+
+
+def train_shard_persistent(shard, num_merges, exchange=None, device=None, table_log2=0, max_ctas=0, timeout_s=0.0):
+    """train_shard with the persistent kernel.  Returns (pairs, counts, ntied, trainer)."""
+    n = shard.numel() if isinstance(shard, torch.Tensor) else len(shard)
+    st = ShardedTrainer(n, num_merges, exchange=exchange, device=device, table_log2=table_log2)
+    try:
+        pairs, counts, ntied = st.train(shard, num_merges, max_ctas=max_ctas, timeout_s=timeout_s)
+        st.ex.barrier()  # nobody unmaps an area a slower peer may still be writing to
+    finally:
+        st.close()
+    return pairs, counts, ntied, st.tr
+
+
+def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0, max_ctas=None, timeout_s=10.0):
+    """The persistent sharded loop with every 'rank' in this process on ONE device: one cooperative kernel per
+    rank on its own stream, all co-resident (max_ctas CTAs each), exchanging through plain device pointers.
+    Exercises the real protocol -- flags, inboxes, shard records -- on a single GPU."""
+    world = len(shards)
+    trs = []
+    for s in shards:
+        n = s.numel() if isinstance(s, torch.Tensor) else len(s)
+        t = Trainer(max(n, 1), num_merges, device=device, table_log2=table_log2)
+        t.load(s)
+        trs.append(t)
+    dev = torch.device("cuda", trs[0].device)
+    if max_ctas is None:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        max_ctas = max(1, (sms * 3) // world)  # 4 CTAs fit per SM: leave one slot of slack
+        max_ctas = min(max_ctas, sms * 2)
+    bbytes, lbytes = trs[0].dist_sizes()
+    all_bnd = torch.zeros(bbytes * world, dtype=torch.uint8, device=dev)
+    all_lst = torch.zeros(lbytes * world, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        areas = [t.peer_area(world)[0] for t in trs]
+        for r, t in enumerate(trs):
+            t.dist_begin(r, world, all_bnd[r * bbytes:(r + 1) * bbytes])
+        torch.cuda.synchronize(dev)
+        for r, t in enumerate(trs):
+            t.dist_count(all_bnd, all_lst[r * lbytes:(r + 1) * lbytes])
+        torch.cuda.synchronize(dev)
+        for t in trs:
+            t.dist_apply(all_lst, world)
+        torch.cuda.synchronize(dev)
+        streams = [torch.cuda.Stream(dev) for _ in trs]
+        for r, t in enumerate(trs):
+            with torch.cuda.stream(streams[r]):
+                t.dist_run(r, world, areas, all_bnd, num_merges, max_ctas=max_ctas, timeout_s=timeout_s)
+        res = [t.results(num_merges) for t in trs]
+    return res, trs
 
 
 def _run_steps(one_step, num_merges, dev, use_graph, warm=3):

@@ -267,6 +267,30 @@ int ecgb_trainer_dist_advance(ecgb_trainer *t, void *stream);
 int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t *h_pairs, uint64_t *h_counts,
                          uint32_t *h_ntied, uint32_t *n_done);
 
+/* Persistent sharded loop (lib.rs:85-117 over a corpus cut into contiguous shards): ONE
+ * cooperative kernel per rank runs every merge step; the per-step exchange is device-initiated --
+ * each rank writes its histogram patches and its 64-byte shard record straight into a receive area in
+ * every peer's memory (NVLink peer stores + flag words), no launches, host calls or collectives inside
+ * the loop.  Set-up (host; the step-wise calls above provide the initial records and histogram):
+ *
+ *   peer_area(world)            -> this rank's receive area             | exchange addresses (IPC handles
+ *                                                                         between processes), BARRIER
+ *   dist_begin / dist_count     -> record, local get_stats              | all-gather each (as above)
+ *   dist_apply(all lists)       -> global histogram on every rank
+ *   dist_run(rank, world, areas, all boundaries, M)   -- asynchronous; every rank must launch
+ *   results()
+ *
+ * A rank whose peer never shows up gives up after timeout_s (default 30 s) and results() reports it.
+ * max_ctas > 0 caps the grid (several ranks co-resident on ONE device: tests). */
+int ecgb_trainer_peer_area(ecgb_trainer *t, int world, void **d_area, uint64_t *bytes);
+int ecgb_trainer_dist_apply(ecgb_trainer *t, const void *d_all_lists, int world, void *stream);
+int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
+                          uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream);
+/* CUDA IPC for the areas of ranks that live in other processes (one process per GPU) */
+int ecgb_ipc_export(const void *d_ptr, uint8_t handle[64]);
+int ecgb_ipc_open(const uint8_t handle[64], int device, void **d_ptr);
+int ecgb_ipc_close(void *d_ptr, int device);
+
 /* expanded sequences of merges given as pairs (lib.rs:101-110); two-call sizing:
  * h_seq_off[n_merges] always receives the total length. */
 int ecgb_expand_merges(const uint32_t *h_pairs, uint32_t n_merges, uint32_t *h_seq, uint64_t seq_cap,

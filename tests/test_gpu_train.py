@@ -170,3 +170,49 @@ def test_sharded_training_one_gpu_many_ranks(oracle, small_corpus):
     sym = oracle.quantize(x[:4], pct["percentile_1"], pct["percentile_99"]).reshape(-1)
     n = sym.size
     _check_sharded(oracle, sym, [n // 4, n // 2, 3 * n // 4], 300)
+
+
+def _check_persistent(oracle, text, cuts, m, max_ctas=None):
+    """dist_loop_kernel: one persistent cooperative kernel per rank, all co-resident on this GPU, exchanging
+    patches / shard records through each other's receive areas (the NVLink protocol with plain pointers)."""
+    from ecgbyte.dist_train import train_shards_persistent_local
+    text = np.ascontiguousarray(text, np.uint8)
+    bounds = [0] + list(cuts) + [len(text)]
+    shards = [text[bounds[r]:bounds[r + 1]].tobytes() for r in range(len(bounds) - 1)]
+    res, trs = train_shards_persistent_local(shards, m, max_ctas=max_ctas)
+    o_ids, o_pairs, o_counts, o_ntied = oracle.train_pairs(text, m, fast=len(text) > 20000)
+    for pairs, counts, ntied in res:  # every rank reports the same merges
+        np.testing.assert_array_equal(pairs, o_pairs)
+        np.testing.assert_array_equal(counts, o_counts)
+        np.testing.assert_array_equal(ntied, o_ntied)
+    ids = np.concatenate([t.ids() for t in trs])
+    np.testing.assert_array_equal(ids, o_ids)
+    assert sum(int(t.lengths(len(o_pairs))[-1]) for t in trs) == len(o_ids)
+
+
+def test_persistent_sharded_loop_one_gpu_many_ranks(oracle, small_corpus):
+    rng = np.random.default_rng(4)
+    text = rng.integers(97, 100, size=5000).astype(np.uint8)
+    _check_persistent(oracle, text, [1700, 3300], 60)
+    _check_persistent(oracle, text, [0, 1, 2, 4999], 40, max_ctas=8)   # empty and single-token shards
+    runs = np.concatenate([np.full(4100, 105, np.uint8), rng.integers(104, 107, size=50).astype(np.uint8),
+                           np.full(8300, 105, np.uint8), np.array([106, 105, 105], np.uint8)])
+    for cuts in ([4096], [4097, 4150], [100, 4200, 12000], [6000, 6001, 6002]):
+        _check_persistent(oracle, runs, cuts, 16, max_ctas=4)    # (x,x) runs across shards, chunks and tile edges
+    x, pct = small_corpus
+    sym = oracle.quantize(x[:4], pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    n = sym.size
+    _check_persistent(oracle, sym, [n // 4, n // 2, 3 * n // 4], 300)
+    _check_persistent(oracle, sym, [n // 3], 300, max_ctas=2)    # few CTAs: several tiles per chunk
+
+
+def test_persistent_sharded_loop_streaming_then_resident(oracle):
+    """A shard too large for the CTAs' shared memory streams through HBM first (look-back pass, halo from the
+    peers' records) and switches to the resident tail later, each rank at its own step."""
+    from ecgbyte import synth
+    x = synth.corpus(7, 6, L=5000, dtype=np.float32)
+    pct = synth.percentiles(x, seed=1)
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+    n = sym.size  # 360 000 symbols; 2 CTAs x 12 288 resident tokens per rank
+    _check_persistent(oracle, sym, [n // 2 - 7], 120, max_ctas=2)
+    _check_persistent(oracle, sym, [n // 5, n // 2], 120, max_ctas=3)
