@@ -68,13 +68,14 @@ struct PairTable {
 };
 
 // Outgoing patch list of one merge step (persistent sharded loop): entry i goes to slot i of this
-// rank's inbox on every peer, written there directly over NVLink.
+// rank's inbox on every peer, written there directly over NVLink as one self-validating 16-byte unit.
 struct PeerPush {
     uint32_t *out_count;       // (local) entries appended so far in this step
     uint32_t *overflow;        // (local) set when the inbox capacity is exceeded
     uint32_t cap;
+    uint32_t tag;              // tag of the step (peer_tag)
     int rank, world;
-    uint2 *dst[kMaxWorld];     // dst[r]: this rank's inbox (for this step's parity) in rank r's memory
+    uint4 *dst[kMaxWorld];     // dst[r]: this rank's inbox (for this step's parity) in rank r's memory
 };
 
 struct Best {
@@ -133,30 +134,38 @@ struct TrainView {
 
 // ---- device-initiated exchange of the persistent sharded loop (dist_loop_kernel) ----
 // Every rank owns a receive AREA in its own memory; peers map it (CUDA IPC between the one-process-per-GPU
-// ranks, or plain pointers inside one process) and write into it directly:
-//   hdr[parity][src]  64 B   flag  = step + 1 once src's patch list and next boundary record for that step are complete,
-//                            count = entries of that list, flag2 = step + 1 once the (x,x) run fields of src's record are in
-//   bd [parity][src]  64 B   Boundary record of src's shard for the stream a step of that parity reads
-//   ent[parity][src][cap]    (key, delta) histogram patches of src's merge pass
-// Two parities: a rank can be at most one step ahead of the slowest peer (it waits for every peer's flag of step t
-// before its argmax of step t + 1).
-struct PeerHdr { uint32_t flag, count, flag2, pad[13]; };
-static_assert(sizeof(PeerHdr) == 64, "header layout");
+// ranks, or plain pointers inside one process) and write into it directly over NVLink.  Everything a peer
+// writes is SELF-VALIDATING (the idea of NCCL's LL protocol): each 8-byte unit carries, next to 4 bytes of
+// payload, the tag of the step it belongs to, and 8-byte stores arrive whole -- so neither side needs a
+// fence (a system-scope fence costs ~5 us here; three per step were most of the step time of the first
+// version of this exchange).  tag = epoch << 20 | (step + 1); the epoch changes with every run, so units
+// left over from an earlier run never validate.
+//   flag[parity][src]     64 B  unit 0: (entries of src's patch list of the step, tag)
+//   rec [parity][src]     64 B  units 0-4: src's shard record of the stream the step with that tag READS --
+//                               (n_lo), (n_hi), (first0 | first1 << 16), (first2 | last0 << 16), (last1);
+//                               unit 5: its (x,x) run fields (trail_par | all_a << 1), second exchange of the step
+//   ent [parity][src][cap] 16 B (key, tag, delta, tag)
+// Two parities: a rank can be at most one step ahead of the slowest peer (it needs every peer's flag of step
+// t before its argmax of step t + 1).
 struct PeerView {
     int rank, world;
     uint32_t cap;                  // list entries per (parity, source)
+    uint32_t epoch;                // run number (see tag)
     uint8_t *area[kMaxWorld];      // area[r] = rank r's area as mapped here; area[rank] is this rank's own
     uint32_t *out_count;           // (local) [2] entries of this rank's outgoing list, by step parity
     uint32_t *done_ctas;           // (local) CTAs that have flushed their patches, cumulative over steps
     uint32_t *overflow;            // (local) outgoing list overflow
     unsigned long long timeout_ns; // a wait for a peer gives up after this long (sets *abort)
 };
-__host__ __device__ inline size_t peer_hdr_off(int world, int parity, int src) { return ((size_t)parity * world + src) * 64; }
-__host__ __device__ inline size_t peer_bd_off(int world, int parity, int src) { return ((size_t)(2 + parity) * world + src) * 64; }
+__host__ __device__ inline size_t peer_flag_off(int world, int parity, int src) { return ((size_t)parity * world + src) * 64; }
+__host__ __device__ inline size_t peer_rec_off(int world, int parity, int src) { return ((size_t)(2 + parity) * world + src) * 64; }
 __host__ __device__ inline size_t peer_ent_off(int world, uint32_t cap, int parity, int src) {
-    return (size_t)4 * world * 64 + ((size_t)parity * world + src) * (size_t)cap * 8;
+    return (size_t)4 * world * 64 + ((size_t)parity * world + src) * (size_t)cap * 16;
 }
 __host__ __device__ inline size_t peer_area_bytes(int world, uint32_t cap) { return peer_ent_off(world, cap, 2, 0); }
+__host__ __device__ inline uint32_t peer_tag(uint32_t epoch, uint32_t step) { return (epoch << 20) | ((step + 1u) & 0xFFFFFu); }
+__host__ __device__ inline unsigned long long peer_unit(uint32_t payload, uint32_t tag) { return (unsigned long long)payload | ((unsigned long long)tag << 32); }
+// payloads of record units 2-4
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k) {
     k ^= k >> 16;
@@ -178,7 +187,7 @@ __device__ __forceinline__ void push_entry(const PeerPush &p, uint32_t key, int 
     base = __shfl_sync(m, base, leader);
     const uint32_t idx = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
     if (idx >= p.cap) { *p.overflow = 1u; return; }
-    const uint2 e = make_uint2(key, (uint32_t)delta);
+    const uint4 e = make_uint4(key, p.tag, (uint32_t)delta, p.tag);
     for (int r = 0; r < p.world; r++)
         if (r != p.rank) p.dst[r][idx] = e;
 }
@@ -496,6 +505,7 @@ struct MergeSmem {
     Boundary bd_near[5];       // resident tail: records of chunks blockIdx-2 .. blockIdx+2
     Boundary bd_peer[kMaxWorld];  // persistent sharded loop: every rank's shard record for this step
     PeerPush push;             // persistent sharded loop: where this step's patches go
+    uint32_t peer_cnt[kMaxWorld];  // persistent sharded loop: entries of each peer's patch list of this step
     // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
     // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
@@ -548,23 +558,26 @@ __device__ __forceinline__ uint32_t stage_index(uint32_t x) { return x ^ ((x >> 
 // merge (lib.rs:10-26) + incremental get_stats.  `upd` receives the histogram patches.
 // TICKETS: tiles are handed out by an atomic counter (any grid size); otherwise tile =
 // blockIdx + k * gridDim, which needs every block to be co-resident (cooperative launch).
-// a wait for a word in this rank's area that a peer writes over NVLink: true once *p == want, false when the
-// wait was abandoned (timeout or another wait already gave up)
-__device__ __forceinline__ bool wait_peer_word(const uint32_t *p, uint32_t want, volatile unsigned int *abort,
-                                               unsigned long long timeout_ns) {
+// Spin until the 8-byte unit at p (this rank's area, written by a peer over NVLink) carries `tag`; returns its
+// payload.  Gives up -- returning 0 with *abort set -- after timeout_ns or when another wait already gave up.
+__device__ __forceinline__ uint32_t wait_unit(const void *p, uint32_t tag, volatile unsigned int *abort,
+                                              unsigned long long timeout_ns, uint32_t where) {
     unsigned long long t0 = 0;
     for (unsigned int spins = 0;; spins++) {
-        uint32_t got;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p) : "memory");
-        if (got == want) return true;
+        unsigned long long u;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(u) : "l"(p) : "memory");
+        if ((uint32_t)(u >> 32) == tag) return (uint32_t)u;
         if ((spins & 255u) == 255u) {
-            if (*abort) return false;
+            if (*abort) return 0u;
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > timeout_ns) { *abort = 1u; return false; }
+            else if (now - t0 > timeout_ns) { *abort = where | 0x80000000u; return 0u; }  // what was being waited for
         }
     }
+}
+__device__ __forceinline__ void st_unit(void *p, uint32_t payload, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(peer_unit(payload, tag)) : "memory");
 }
 
 template <bool TICKETS, bool RESIDENT>
@@ -591,23 +604,33 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     if (sharded) {
         const int par = (int)(step & 1u);
         const uint8_t *mine = pv->area[pv->rank];
-        if (same) {  // the run fields of the peers' records arrive in this step's second exchange
-            if (threadIdx.x < (unsigned)pv->world && (int)threadIdx.x != pv->rank)
-                wait_peer_word(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv->world, par, (int)threadIdx.x))->flag2,
-                               step + 1u, v.abort, pv->timeout_ns);
-            __syncthreads();
+        const uint32_t tag = peer_tag(pv->epoch, step);
+        if (threadIdx.x < (unsigned)pv->world * 8u) {
+            // the peers' shard records for this step's stream, one thread per unit (the run fields arrive in the
+            // second exchange of an (x,x) step)
+            const int r = (int)(threadIdx.x >> 3), u = (int)(threadIdx.x & 7u);
+            if (r != pv->rank && (u < 5 || (u == 5 && same))) {
+                const uint32_t val = wait_unit(mine + peer_rec_off(pv->world, par, r) + 8 * u, tag, v.abort, pv->timeout_ns,
+                                               (1u << 28) | ((uint32_t)u << 24) | ((uint32_t)r << 20) | (step & 0xFFFFFu));
+                Boundary &bd = sm.bd_peer[r];
+                if (u == 0) bd.n_lo = val;
+                else if (u == 1) bd.n_hi = val;
+                else if (u == 2) { bd.first[0] = val & 0xFFFFu; bd.first[1] = val >> 16; }
+                else if (u == 3) { bd.first[2] = val & 0xFFFFu; bd.last[0] = val >> 16; }
+                else if (u == 4) bd.last[1] = val;
+                else { bd.trail_par = val & 1u; bd.all_a = (val >> 1) & 1u; }
+            }
         }
-        for (int i = threadIdx.x; i < pv->world * kBoundaryWords; i += kTPB)
-            reinterpret_cast<uint32_t *>(sm.bd_peer)[i] = __ldcg(reinterpret_cast<const uint32_t *>(mine + peer_bd_off(pv->world, par, 0)) + i);
-        if (threadIdx.x == 0) {  // this step's patches: local table + every peer's inbox
+        if (threadIdx.x == kTPB - 1) {  // this step's patches: local table + every peer's inbox
             PeerPush &pp = sm.push;
             pp.out_count = pv->out_count + par;
             pp.overflow = pv->overflow;
             pp.cap = pv->cap;
+            pp.tag = tag;
             pp.rank = pv->rank;
             pp.world = pv->world;
             for (int r = 0; r < pv->world; r++)
-                pp.dst[r] = reinterpret_cast<uint2 *>(pv->area[r] + peer_ent_off(pv->world, pv->cap, par, pv->rank));
+                pp.dst[r] = reinterpret_cast<uint4 *>(pv->area[r] + peer_ent_off(pv->world, pv->cap, par, pv->rank));
         }
     }
     if (resident) {
@@ -1143,9 +1166,6 @@ __global__ void __launch_bounds__(kTPB, kCtasPerSm) train_loop_kernel(TrainView 
 // ------------------------------------------------------------------ persistent sharded loop
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t val) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(val) : "memory");
-}
 
 // Record of this rank's shard as the stream that step s reads, without the (x,x) run fields.  One thread;
 // everything it reads was written by other CTAs of this grid before they arrived at the counter the caller
@@ -1231,19 +1251,18 @@ __device__ void shard_run_fields(const TrainView &v, uint32_t s, bool resident, 
 // to finish publishes the shard record of the next stream and raises the step's flag on the peers.  Then
 // every rank applies the patches the peers left in its area.  One exchange per step ((x,x) steps add one
 // for the run parities), no launches, no host, no collective library inside the loop.
-__global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_loop_kernel(TrainView v, PeerView pv, uint32_t n_steps) {
-    __shared__ MergeSmem sm;
-    __shared__ Best s_best;
-    __shared__ int s_last;
-    extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
+__device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerView &pv, uint32_t n_steps, MergeSmem &sm, Best &s_best,
+                                               int &s_last, uint16_t *chunk) {
     AbortableGrid grid{v.gbar, v.abort, 0u};
     volatile unsigned int *abort = v.abort;
     bool res_mode = false, res_fresh = false;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
     uint8_t *const mine = pv.area[pv.rank];
+    ECGB_MARK_DECL;
     uint32_t step = 0;
     for (; step < n_steps; step++) {
+        ECGB_MARK_RESET;
         if (*abort) break;
         if (!res_mode && v.resident_ok) {
             // the shard now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
@@ -1281,68 +1300,133 @@ __global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_loop_kernel(TrainView v
             // second exchange of an (x,x) step: the run fields of this shard's record
             uint32_t tp = 0, alla = 0;
             shard_run_fields(v, step, res_mode, a, &tp, &alla);
-            if (threadIdx.x == 0) {
-                for (int r = 0; r < pv.world; r++) {
-                    Boundary *dst = reinterpret_cast<Boundary *>(pv.area[r] + peer_bd_off(pv.world, par, pv.rank));
-                    dst->trail_par = tp;
-                    dst->all_a = alla;
-                }
-                __threadfence_system();
-                for (int r = 0; r < pv.world; r++)
-                    if (r != pv.rank)
-                        st_release_sys(&reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->flag2, step + 1u);
-            }
+            tp = __shfl_sync(0xffffffffu, tp, 0);
+            alla = __shfl_sync(0xffffffffu, alla, 0);
+            if ((int)threadIdx.x < pv.world && (int)threadIdx.x != pv.rank)  // lane r serves peer r
+                st_unit(pv.area[threadIdx.x] + peer_rec_off(pv.world, par, pv.rank) + 8 * 5, tp | (alla << 1), peer_tag(pv.epoch, step));
         }
+        ECGB_MARK(0);
         if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (size_t)par * v.cta_stride, v.main, sm, chunk, &pv);
         else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr, &pv);
-        // this CTA's patches are in the local table and on their way to the peers
-        __threadfence_system();
+        ECGB_MARK_RESET;
+        // this CTA's patches are in the local table (device-scope fence: the last CTA to arrive reads the list
+        // length and the chunk records) and on their way to the peers (self-validating, no fence)
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();
             const unsigned int old = atomicAdd(pv.done_ctas, 1u);
             s_last = old == (step + 1u) * gridDim.x - 1u;
         }
         __syncthreads();
-        if (s_last && threadIdx.x == 0) {
-            // the whole rank has finished the pass: shard record of the next stream, list length, flag
+        ECGB_MARK(11);
+        if (s_last && threadIdx.x < 32) {
+            // the whole rank has finished the pass: shard record of the next stream, list length, flag (warp 0)
+            const int lane = threadIdx.x;
             __threadfence();
-            Boundary bd;
-            shard_record(v, step + 1u, res_mode, &bd);
+            Boundary *rec = &sm.bd_near[0];  // free between passes
+            bool fast = false;
+            if (res_mode) {
+                // usual case: the first chunk holds >= 3 tokens and the last one >= 2 -- both records in one round trip
+                const Boundary *cb = v.cta_bd + (size_t)(par ^ 1) * v.cta_stride;
+                const uint32_t val = ld_vol(reinterpret_cast<const uint32_t *>(lane < 16 ? &cb[0] : &cb[gridDim.x - 1]) + (lane & 15));
+                const unsigned long long n = *reinterpret_cast<const volatile unsigned long long *>(&v.n_hist[step + 1u]);
+                const uint32_t n0 = __shfl_sync(0xffffffffu, val, 0), nl = __shfl_sync(0xffffffffu, val, 16);
+                const uint32_t l0 = __shfl_sync(0xffffffffu, val, 16 + 5), l1 = __shfl_sync(0xffffffffu, val, 16 + 6);
+                fast = n0 >= 3 && nl >= 2;
+                if (fast && lane < 16) {
+                    uint32_t w = 0;
+                    if (lane == 0) w = (uint32_t)n;
+                    else if (lane == 1) w = (uint32_t)(n >> 32);
+                    else if (lane <= 4) w = val;  // first[0..2] of chunk 0
+                    else if (lane == 5) w = l0;
+                    else if (lane == 6) w = l1;
+                    reinterpret_cast<uint32_t *>(rec)[lane] = w;
+                }
+            }
+            if (!fast && lane == 0) shard_record(v, step + 1u, res_mode, rec);
+            __syncwarp();
             uint32_t cnt = ld_vol(pv.out_count + par);
             if (cnt > pv.cap) cnt = pv.cap;  // overflow was flagged by push_entry
-            pv.out_count[par ^ 1] = 0u;     // nobody appends before the barrier that ends this step
-            for (int r = 0; r < pv.world; r++) {
-                uint32_t *dst = reinterpret_cast<uint32_t *>(pv.area[r] + peer_bd_off(pv.world, par ^ 1, pv.rank));
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(&bd);
-#pragma unroll
-                for (int w = 0; w < kBoundaryWords; w++) dst[w] = src[w];
-                if (r != pv.rank) reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->count = cnt;
+            if (lane == 0) pv.out_count[par ^ 1] = 0u;  // nobody appends before the barrier that ends this step
+            if (lane < 5) {  // record of the stream step + 1 reads, unit `lane`, to every peer
+                const uint32_t pay = lane == 0 ? rec->n_lo : lane == 1 ? rec->n_hi : lane == 2 ? (rec->first[0] | (rec->first[1] << 16))
+                                   : lane == 3 ? (rec->first[2] | (rec->last[0] << 16)) : rec->last[1];
+                const uint32_t tag_next = peer_tag(pv.epoch, step + 1u);
+                for (int r = 0; r < pv.world; r++)
+                    if (r != pv.rank) st_unit(pv.area[r] + peer_rec_off(pv.world, par ^ 1, pv.rank) + 8 * lane, pay, tag_next);
             }
-            __threadfence_system();
-            for (int r = 0; r < pv.world; r++)
-                if (r != pv.rank) st_release_sys(&reinterpret_cast<PeerHdr *>(pv.area[r] + peer_hdr_off(pv.world, par, pv.rank))->flag, step + 1u);
+            if (lane < pv.world && lane != pv.rank)  // lane r serves peer r: the step's flag with the list length
+                st_unit(pv.area[lane] + peer_flag_off(pv.world, par, pv.rank), cnt, peer_tag(pv.epoch, step));
         }
         // the peers' patches of this step
-        if (threadIdx.x < (unsigned)pv.world && (int)threadIdx.x != pv.rank)
-            wait_peer_word(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv.world, par, (int)threadIdx.x))->flag, step + 1u, abort,
-                           pv.timeout_ns);
+        if (threadIdx.x < (unsigned)pv.world) {
+            uint32_t cnt = 0;
+            if ((int)threadIdx.x != pv.rank)
+                cnt = wait_unit(mine + peer_flag_off(pv.world, par, (int)threadIdx.x), peer_tag(pv.epoch, step), abort, pv.timeout_ns,
+                                (2u << 28) | (threadIdx.x << 20) | (step & 0xFFFFFu));
+            sm.peer_cnt[threadIdx.x] = min(cnt, pv.cap);
+        }
         __syncthreads();
+        ECGB_MARK(12);
         {
-            const unsigned long long tau_val = __ldcg(v.main.tau);
+            const unsigned long long tau_val = sm.tau_val;  // read by the pass; tau only changes inside the argmax
+            const uint32_t tag = peer_tag(pv.epoch, step);
             for (int r = 0; r < pv.world; r++) {
                 if (r == pv.rank) continue;
-                const uint32_t cnt = min(__ldcg(&reinterpret_cast<const PeerHdr *>(mine + peer_hdr_off(pv.world, par, r))->count), pv.cap);
-                const uint2 *ent = reinterpret_cast<const uint2 *>(mine + peer_ent_off(pv.world, pv.cap, par, r));
+                const uint32_t cnt = sm.peer_cnt[r];
+                const uint4 *ent = reinterpret_cast<const uint4 *>(mine + peer_ent_off(pv.world, pv.cap, par, r));
                 for (uint64_t i = gtid; i < cnt; i += gthreads) {
-                    const uint2 e = __ldcg(ent + i);
-                    table_add(v.main, e.x, (long long)(int)e.y, tau_val);
+                    // an entry may still be in flight behind the flag: both halves carry the tag
+                    uint4 e;
+                    unsigned long long t0 = 0;
+                    for (unsigned int spins = 0;; spins++) {
+                        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(ent + i) : "memory");
+                        if (e.y == tag && e.w == tag) break;
+                        if ((spins & 255u) == 255u) {
+                            if (*abort) break;
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > pv.timeout_ns) { *abort = 0x80000000u | (3u << 28) | ((uint32_t)r << 20) | (step & 0xFFFFFu); break; }
+                        }
+                    }
+                    table_add(v.main, e.x, (long long)(int)e.z, tau_val);
                 }
             }
         }
+        ECGB_MARK(13);
         grid.sync();
+        ECGB_MARK(10);
     }
     if (res_mode) resident_write_back(grid, v, step, sm.chunk_n, chunk);
     if (gtid == 0) v.dev->cur_step = step;
+}
+
+__global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_loop_kernel(TrainView v, PeerView pv, uint32_t n_steps) {
+    __shared__ MergeSmem sm;
+    __shared__ Best s_best;
+    __shared__ int s_last;
+    extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
+    dist_loop_body(v, pv, n_steps, sm, s_best, s_last, chunk);
+}
+
+// Every rank of a run in ONE cooperative launch on one device (blockIdx.y = rank): the co-residency the ranks'
+// spin waits rely on is then guaranteed by the launch itself.  Same body, same protocol; used to exercise the
+// exchange on a single GPU (tests).
+struct DistLaunch {
+    TrainView v;
+    PeerView pv;
+};
+__global__ void __launch_bounds__(kTPB, kCtasPerSm) dist_loop_local_kernel(const DistLaunch *__restrict__ ranks, uint32_t n_steps) {
+    __shared__ MergeSmem sm;
+    __shared__ Best s_best;
+    __shared__ int s_last;
+    __shared__ DistLaunch s_me;
+    extern __shared__ __align__(16) uint16_t chunk[];
+    for (uint32_t i = threadIdx.x; i < sizeof(DistLaunch) / 4; i += kTPB)
+        reinterpret_cast<uint32_t *>(&s_me)[i] = reinterpret_cast<const uint32_t *>(&ranks[blockIdx.y])[i];
+    __syncthreads();
+    dist_loop_body(s_me.v, s_me.pv, n_steps, sm, s_best, s_last, chunk);
 }
 
 // Sharded training: the argmax of one step as a cooperative launch (candidate list instead of a full
@@ -1455,8 +1539,21 @@ struct ecgb_trainer {
     uint64_t peer_bytes = 0;
     int peer_world = 0;
     uint32_t peer_cap = 0;
+    uint32_t peer_epoch = 0;       // run number, part of every unit's tag
     uint32_t *peer_ctr = nullptr;  // out_count[2], done_ctas, overflow
 };
+
+static void print_phases() {
+#ifdef ECGB_TRAIN_TIMING
+    unsigned long long ph[16], zero[16] = {0};
+    cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph));
+    cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
+    static const char *names[14] = {"argmax", "pass setup", "tile load+sync", "flags+patches", "scan+sync", "stage",
+                                    "look-back", "sync", "write-out", "patch flush", "grid sync", "fence+arrive",
+                                    "wait peers", "apply"};
+    for (int i = 0; i < 14; i++) fprintf(stderr, "phase %-14s %10.3f ms\n", names[i], ph[i] * 1e-6);
+#endif
+}
 
 static int dev_alloc(ecgb_trainer *t, void **p, size_t bytes, bool zero) {
     if (t->n_blocks >= (int)(sizeof(t->blocks) / sizeof(t->blocks[0]))) return fail(ECGB_ECUDA, "trainer allocation table full");
@@ -1621,7 +1718,12 @@ static int check_tables(ecgb_trainer *t) {
     if (dflags[1]) return fail(ECGB_ECAPACITY, "delta table overflow");
     uint32_t sync_words[3] = {0, 0, 0};  // arrive, gbar, abort
     ECGB_CUDA(cudaMemcpy(sync_words, t->v.arrive, 12, cudaMemcpyDeviceToHost));
-    if (sync_words[2]) return fail(ECGB_ECUDA, "sharded training: a wait for a peer rank timed out (is every rank running?)");
+    if (sync_words[2]) {
+        const uint32_t w = sync_words[2];
+        static const char *what[4] = {"?", "shard record", "step flag", "patch entry"};
+        return fail(ECGB_ECUDA, "sharded training: the wait for a %s (unit %u) of rank %u in step %u timed out -- is every rank running?",
+                    what[(w >> 28) & 3u], (w >> 24) & 15u, (w >> 20) & 15u, w & 0xFFFFFu);
+    }
     if (t->peer_ctr) {
         uint32_t ctr[4] = {0, 0, 0, 0};
         ECGB_CUDA(cudaMemcpy(ctr, t->peer_ctr, 16, cudaMemcpyDeviceToHost));
@@ -1665,16 +1767,7 @@ extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *
     }
     ECGB_CUDA(cudaGetLastError());
     ECGB_CUDA(cudaStreamSynchronize(st));
-#ifdef ECGB_TRAIN_TIMING
-    {
-        unsigned long long ph[16], zero[16] = {0};
-        cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph));
-        cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
-        static const char *names[11] = {"argmax", "pass setup", "tile load+sync", "flags+patches", "scan+sync", "stage",
-                                        "look-back", "sync", "write-out", "patch flush", "grid sync"};
-        for (int i = 0; i < 11; i++) fprintf(stderr, "phase %-14s %10.3f ms\n", names[i], ph[i] * 1e-6);
-    }
-#endif
+    print_phases();
     int rc = check_tables(t);
     if (rc) return rc;
     DevState hs;
@@ -1885,18 +1978,19 @@ extern "C" int ecgb_trainer_peer_area(ecgb_trainer *t, int world, void **d_area,
     ECGB_REQUIRE(t && d_area && bytes, "NULL argument");
     ECGB_REQUIRE(world >= 1 && world <= kMaxWorld, "world %d out of range [1, %d]", world, kMaxWorld);
     DeviceGuard g(t->device);
-    const uint32_t cap = 1u << 20;  // patch entries per (parity, source): 8 MB each
+    const uint32_t cap = 1u << 20;  // patch entries per (parity, source): 16 MB each
     const uint64_t need = peer_area_bytes(world, cap);
     if (t->peer_area == nullptr || t->peer_world != world) {
         ECGB_REQUIRE(t->peer_area == nullptr, "the receive area was created for %d ranks", t->peer_world);
-        int rc = dev_alloc(t, (void **)&t->peer_area, need, false);
+        int rc = dev_alloc(t, (void **)&t->peer_area, need, true);
         if (!rc) rc = dev_alloc(t, (void **)&t->peer_ctr, 16, true);
         if (rc) return rc;
         t->peer_bytes = need;
         t->peer_world = world;
         t->peer_cap = cap;
     }
-    // headers and records only: list entries are never read beyond the published count
+    // flags and records; list entries validate themselves through the run's epoch
+    t->peer_epoch = (t->peer_epoch % 4095u) + 1u;
     ECGB_CUDA(cudaMemset(t->peer_area, 0, peer_ent_off(world, cap, 0, 0)));
     ECGB_CUDA(cudaMemset(t->peer_ctr, 0, 16));
     ECGB_CUDA(cudaDeviceSynchronize());
@@ -1950,28 +2044,35 @@ extern "C" int ecgb_trainer_dist_apply(ecgb_trainer *t, const void *d_all_lists,
 // d_areas[r] = rank r's receive area as addressable from this process; d_all_boundaries = the gathered
 // records of ecgb_trainer_dist_begin.  The table must hold the global histogram (dist_count + dist_apply).
 // Read the outcome with ecgb_trainer_results.
-extern "C" int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
-                                     uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream) {
+static int dist_prepare(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
+                        uint32_t num_merges, double timeout_s, cudaStream_t st, TrainView *view_out, PeerView *pv_out) {
     ECGB_REQUIRE(t && d_areas && d_all_boundaries, "NULL argument");
     ECGB_REQUIRE(t->loaded && t->steps_done == 0 && !t->device_steps, "load the shard first");
     ECGB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
     ECGB_REQUIRE(t->peer_area != nullptr && t->peer_world == world, "call ecgb_trainer_peer_area(world) first");
     ECGB_REQUIRE(d_areas[rank] == t->peer_area, "d_areas[rank] must be this trainer's own area");
     ECGB_REQUIRE(num_merges <= t->max_merges, "num_merges %u > max_merges %u", num_merges, t->max_merges);
-    DeviceGuard g(t->device);
-    cudaStream_t st = as_stream(stream);
     t->v.rank = rank;
     t->v.world = world;
-    // the records of the initial stream (step 0 reads parity 0)
-    ECGB_CUDA(cudaMemcpyAsync(t->peer_area + peer_bd_off(world, 0, 0), d_all_boundaries, sizeof(Boundary) * (size_t)world,
-                              cudaMemcpyDeviceToDevice, st));
-    int per_sm = 0;
-    const size_t dyn_smem = (size_t)kChunkCap * sizeof(uint16_t);
-    ECGB_CUDA(cudaFuncSetAttribute(dist_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_loop_kernel, kTPB, dyn_smem));
-    if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "dist_loop_kernel does not fit on this device");
-    int grid = std::min(t->sms * std::min(per_sm, kCtasPerSm), (int)t->v.cta_stride);
-    if (max_ctas > 0) grid = std::min(grid, (int)max_ctas);
+    // the records of the initial stream (step 0 reads parity 0), as tagged units
+    {
+        std::vector<Boundary> all((size_t)world);
+        ECGB_CUDA(cudaMemcpyAsync(all.data(), d_all_boundaries, sizeof(Boundary) * all.size(), cudaMemcpyDeviceToHost, st));
+        ECGB_CUDA(cudaStreamSynchronize(st));
+        std::vector<unsigned long long> units((size_t)world * 8, 0ull);
+        const uint32_t tag = peer_tag(t->peer_epoch, 0);
+        for (int r = 0; r < world; r++) {
+            const Boundary &bd = all[r];
+            unsigned long long *u = &units[(size_t)r * 8];
+            u[0] = peer_unit(bd.n_lo, tag);
+            u[1] = peer_unit(bd.n_hi, tag);
+            u[2] = peer_unit((bd.first[0] & 0xFFFFu) | (bd.first[1] << 16), tag);
+            u[3] = peer_unit((bd.first[2] & 0xFFFFu) | (bd.last[0] << 16), tag);
+            u[4] = peer_unit(bd.last[1], tag);
+        }
+        ECGB_CUDA(cudaMemcpyAsync(t->peer_area + peer_rec_off(world, 0, 0), units.data(), units.size() * 8, cudaMemcpyHostToDevice, st));
+        ECGB_CUDA(cudaStreamSynchronize(st));
+    }
     TrainView view = t->v;
     view.redundant_max = kRedundantArgmax;
     const char *knob = getenv("ECGB_RESIDENT_TAIL");
@@ -1980,6 +2081,7 @@ extern "C" int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void 
     pv.rank = rank;
     pv.world = world;
     pv.cap = t->peer_cap;
+    pv.epoch = t->peer_epoch;
     for (int r = 0; r < world; r++) {
         ECGB_REQUIRE(d_areas[r] != nullptr, "d_areas[%d] is NULL", r);
         pv.area[r] = static_cast<uint8_t *>(d_areas[r]);
@@ -1988,11 +2090,78 @@ extern "C" int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void 
     pv.done_ctas = t->peer_ctr + 2;
     pv.overflow = t->peer_ctr + 3;
     pv.timeout_ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 30.0) * 1e9);
+    *view_out = view;
+    *pv_out = pv;
+    return ECGB_OK;
+}
+
+template <class K>
+static int dist_grid(const ecgb_trainer *t, K kernel, uint32_t max_ctas, int ranks_on_device, int *grid_out) {
+    int per_sm = 0;
+    const size_t dyn_smem = (size_t)kChunkCap * sizeof(uint16_t);
+    ECGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    ECGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTPB, dyn_smem));
+    if (per_sm < 1) return fail(ECGB_EUNSUPPORTED, "the persistent sharded kernel does not fit on this device");
+    int grid = std::min(t->sms * std::min(per_sm, kCtasPerSm), (int)t->v.cta_stride) / ranks_on_device;
+    if (max_ctas > 0) grid = std::min(grid, (int)max_ctas);
+    if (grid < 1) return fail(ECGB_EUNSUPPORTED, "%d ranks do not fit on one device", ranks_on_device);
+    *grid_out = grid;
+    return ECGB_OK;
+}
+
+// Launch the persistent sharded loop of this rank (asynchronous; every rank of the run must launch, each on
+// its own device).  d_areas[r] = rank r's receive area as addressable from this process; d_all_boundaries =
+// the gathered records of ecgb_trainer_dist_begin.  The table must hold the global histogram (dist_count +
+// dist_apply).  Read the outcome with ecgb_trainer_results.
+extern "C" int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
+                                     uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream) {
+    ECGB_REQUIRE(t, "NULL argument");
+    DeviceGuard g(t->device);
+    cudaStream_t st = as_stream(stream);
+    TrainView view;
+    PeerView pv;
+    int rc = dist_prepare(t, rank, world, d_areas, d_all_boundaries, num_merges, timeout_s, st, &view, &pv);
+    if (rc) return rc;
+    int grid = 0;
+    rc = dist_grid(t, dist_loop_kernel, max_ctas, 1, &grid);
+    if (rc) return rc;
     uint32_t steps = num_merges;
     void *kargs[] = {&view, &pv, &steps};
-    ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)dist_loop_kernel, dim3(grid), dim3(kTPB), kargs, dyn_smem, st));
+    ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)dist_loop_kernel, dim3(grid), dim3(kTPB), kargs,
+                                          (size_t)kChunkCap * sizeof(uint16_t), st));
     ECGB_CUDA(cudaGetLastError());
     t->device_steps = true;
+    return ECGB_OK;
+}
+
+// The same run with every rank on ONE device, as one cooperative launch (blockIdx.y = rank) so that all ranks
+// are co-resident by construction: ts[r] is rank r's trainer (all on the same device), d_areas[r] its area.
+extern "C" int ecgb_trainer_dist_run_local(ecgb_trainer *const *ts, int world, void *const *d_areas, const void *d_all_boundaries,
+                                           uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream) {
+    ECGB_REQUIRE(ts && world >= 1 && world <= kMaxWorld, "bad arguments");
+    for (int r = 0; r < world; r++) ECGB_REQUIRE(ts[r] && ts[r]->device == ts[0]->device, "every trainer must live on the same device");
+    DeviceGuard g(ts[0]->device);
+    cudaStream_t st = as_stream(stream);
+    std::vector<DistLaunch> h((size_t)world);
+    for (int r = 0; r < world; r++) {
+        int rc = dist_prepare(ts[r], r, world, d_areas, d_all_boundaries, num_merges, timeout_s, st, &h[r].v, &h[r].pv);
+        if (rc) return rc;
+    }
+    int grid = 0;
+    int rc = dist_grid(ts[0], dist_loop_local_kernel, max_ctas, world, &grid);
+    if (rc) return rc;
+    DistLaunch *d_ranks = nullptr;
+    rc = dev_alloc(ts[0], (void **)&d_ranks, sizeof(DistLaunch) * (size_t)world, false);  // lives as long as rank 0's trainer
+    if (rc) return rc;
+    ECGB_CUDA(cudaMemcpyAsync(d_ranks, h.data(), sizeof(DistLaunch) * (size_t)world, cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    uint32_t steps = num_merges;
+    const DistLaunch *arg0 = d_ranks;
+    void *kargs[] = {&arg0, &steps};
+    ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)dist_loop_local_kernel, dim3(grid, world), dim3(kTPB), kargs,
+                                          (size_t)kChunkCap * sizeof(uint16_t), st));
+    ECGB_CUDA(cudaGetLastError());
+    for (int r = 0; r < world; r++) ts[r]->device_steps = true;
     return ECGB_OK;
 }
 
@@ -2017,6 +2186,7 @@ extern "C" int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t 
     if (rc) return rc;
     DevState hs;
     ECGB_CUDA(cudaMemcpy(&hs, t->v.dev, sizeof(hs), cudaMemcpyDeviceToHost));
+    if (t->peer_area != nullptr) print_phases();
     if (t->device_steps) {  // steps were driven by the device-side counter
         t->steps_done = std::min(hs.cur_step, t->max_merges);
         t->argmax_for = t->steps_done;

@@ -80,6 +80,7 @@ def _declare(L):
         "ecgb_trainer_peer_area": ([vp, i32, pp, C.POINTER(u64)], i32),
         "ecgb_trainer_dist_apply": ([vp, vp, i32, vp], i32),
         "ecgb_trainer_dist_run": ([vp, i32, i32, pp, vp, u32, u32, dbl, vp], i32),
+        "ecgb_trainer_dist_run_local": ([pp, i32, pp, vp, u32, u32, dbl, vp], i32),
         "ecgb_ipc_export": ([vp, vp], i32),
         "ecgb_ipc_open": ([vp, i32, pp], i32),
         "ecgb_ipc_close": ([vp, i32], i32),

@@ -163,10 +163,12 @@ def train_shard_persistent(shard, num_merges, exchange=None, device=None, table_
     return pairs, counts, ntied, st.tr
 
 
-def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0, max_ctas=None, timeout_s=10.0):
-    """The persistent sharded loop with every 'rank' in this process on ONE device: one cooperative kernel per
-    rank on its own stream, all co-resident (max_ctas CTAs each), exchanging through plain device pointers.
-    Exercises the real protocol -- flags, inboxes, shard records -- on a single GPU."""
+def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0, max_ctas=0, timeout_s=10.0):
+    """The persistent sharded loop with every 'rank' in this process on ONE device, as ONE cooperative launch
+    (blockIdx.y = rank, so all ranks are co-resident by construction), exchanging through plain device
+    pointers.  Exercises the real protocol -- tagged units, inboxes, shard records -- on a single GPU."""
+    import ctypes as C
+    from . import _lib
     world = len(shards)
     trs = []
     for s in shards:
@@ -175,10 +177,6 @@ def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0,
         t.load(s)
         trs.append(t)
     dev = torch.device("cuda", trs[0].device)
-    if max_ctas is None:
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        max_ctas = max(1, (sms * 3) // world)  # 4 CTAs fit per SM: leave one slot of slack
-        max_ctas = min(max_ctas, sms * 2)
     bbytes, lbytes = trs[0].dist_sizes()
     all_bnd = torch.zeros(bbytes * world, dtype=torch.uint8, device=dev)
     all_lst = torch.zeros(lbytes * world, dtype=torch.uint8, device=dev)
@@ -193,10 +191,11 @@ def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0,
         for t in trs:
             t.dist_apply(all_lst, world)
         torch.cuda.synchronize(dev)
-        streams = [torch.cuda.Stream(dev) for _ in trs]
-        for r, t in enumerate(trs):
-            with torch.cuda.stream(streams[r]):
-                t.dist_run(r, world, areas, all_bnd, num_merges, max_ctas=max_ctas, timeout_s=timeout_s)
+        hs = (C.c_void_p * world)(*[t._h for t in trs])
+        ar = (C.c_void_p * world)(*[C.c_void_p(a) for a in areas])
+        _lib.check(_lib.lib().ecgb_trainer_dist_run_local(hs, world, ar, C.c_void_p(all_bnd.data_ptr()), int(num_merges),
+                                                          int(max_ctas), float(timeout_s),
+                                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         res = [t.results(num_merges) for t in trs]
     return res, trs
 

@@ -93,3 +93,18 @@ def corpus_cuda(seed, n, L=5000, dtype=None, device=None, start=0, chunk=2048):
         else:
             out[c0:c0 + m] = x.to(dtype)
     return out
+
+
+def corpus_cuda_range(seed, n_total, lo, hi, L=5000, dtype=None, device=None, chunk=2048):
+    """Records [lo, hi) of corpus_cuda(seed, n_total, ...) without generating the rest: the generator is seeded
+    per chunk of `chunk` records, so a rank of a sharded run rebuilds exactly its slice of the one corpus."""
+    import torch
+    dtype = dtype or torch.float32
+    device = torch.device(device if device is not None else "cuda")
+    out = torch.empty((max(hi - lo, 0), N_LEADS, L), dtype=dtype, device=device)
+    for c0 in range((lo // chunk) * chunk, hi, chunk):
+        m = min(chunk, n_total - c0)
+        x = corpus_cuda(seed, m, L, dtype, device, start=c0, chunk=chunk)
+        a, b = max(lo, c0), min(hi, c0 + m)
+        out[a - lo:b - lo] = x[a - c0:b - c0]
+    return out

@@ -281,11 +281,14 @@ int ecgb_trainer_results(ecgb_trainer *t, uint32_t n_steps, uint32_t *h_pairs, u
  *   results()
  *
  * A rank whose peer never shows up gives up after timeout_s (default 30 s) and results() reports it.
- * max_ctas > 0 caps the grid (several ranks co-resident on ONE device: tests). */
+ * max_ctas > 0 caps the grid. */
 int ecgb_trainer_peer_area(ecgb_trainer *t, int world, void **d_area, uint64_t *bytes);
 int ecgb_trainer_dist_apply(ecgb_trainer *t, const void *d_all_lists, int world, void *stream);
 int ecgb_trainer_dist_run(ecgb_trainer *t, int rank, int world, void *const *d_areas, const void *d_all_boundaries,
                           uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream);
+/* every rank on ONE device as one cooperative launch (co-residency by construction): ts[r] = rank r's trainer */
+int ecgb_trainer_dist_run_local(ecgb_trainer *const *ts, int world, void *const *d_areas, const void *d_all_boundaries,
+                                uint32_t num_merges, uint32_t max_ctas, double timeout_s, void *stream);
 /* CUDA IPC for the areas of ranks that live in other processes (one process per GPU) */
 int ecgb_ipc_export(const void *d_ptr, uint8_t handle[64]);
 int ecgb_ipc_open(const uint8_t handle[64], int device, void **d_ptr);

@@ -179,7 +179,7 @@ def _check_persistent(oracle, text, cuts, m, max_ctas=None):
     text = np.ascontiguousarray(text, np.uint8)
     bounds = [0] + list(cuts) + [len(text)]
     shards = [text[bounds[r]:bounds[r + 1]].tobytes() for r in range(len(bounds) - 1)]
-    res, trs = train_shards_persistent_local(shards, m, max_ctas=max_ctas)
+    res, trs = train_shards_persistent_local(shards, m, max_ctas=max_ctas or 0)
     o_ids, o_pairs, o_counts, o_ntied = oracle.train_pairs(text, m, fast=len(text) > 20000)
     for pairs, counts, ntied in res:  # every rank reports the same merges
         np.testing.assert_array_equal(pairs, o_pairs)
