@@ -1083,10 +1083,59 @@ __device__ __forceinline__ Best grid_argmax(Grid &grid, const TrainView &v, Best
     return fin;
 }
 
-// Resident tail, end of the run: back to one contiguous stream in tok[step & 1] (step = merges done),
-// where the host expects it.
+// Where a CTA's piece of the token stream lives in the persistent kernels.  Default (resident_ok = 2): the
+// stream is cut into one contiguous chunk per CTA before the first step and stays that way -- each chunk is
+// merged in place, in the first token buffer while it is longer than kChunkCap and in the CTA's shared memory
+// from then on (every CTA moves on its own: the neighbours only ever see its boundary record).  No output
+// offsets, hence no look-back chain, no second buffer, and the CTAs stream independently of each other.
+// resident_ok = 1: the round-1 scheme (one stream, ping-pong buffers, decoupled look-back; chunks only once
+// the whole stream fits in shared memory); 0: never chunk.  Both kept for A/B runs (ECGB_RESIDENT_TAIL).
+struct ChunkWhere {
+    uint16_t *g = nullptr;   // the chunk's region in the first token buffer (chunked from the start)
+    bool res_mode = false;   // the stream is held as chunks
+    bool in_smem = false;    // this CTA's chunk is in shared memory
+    bool fresh = false;      // chunks were just formed: no boundary records published yet
+    bool from_start = false; // resident_ok = 2
+};
+
+__device__ __forceinline__ void chunk_step_begin(const TrainView &v, uint32_t step, MergeSmem &sm, uint16_t *chunk_smem, ChunkWhere &w) {
+    if (!w.res_mode && v.resident_ok == 2u && step == 0) {
+        const unsigned long long n = v.dev->n[0];
+        const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;  // 16-byte aligned chunk starts
+        const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
+        const unsigned long long hi = min(n, lo + clen);
+        w.g = v.tok[0] + lo;
+        if (threadIdx.x == 0) sm.chunk_n = (int)(hi - lo);
+        w.res_mode = w.fresh = w.from_start = true;
+        __syncthreads();
+    } else if (!w.res_mode && v.resident_ok == 1u) {
+        // the stream now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
+        const unsigned long long n = v.dev->n[step & 1];
+        const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;
+        if (clen <= (unsigned long long)kChunkCap) {
+            const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
+            const unsigned long long hi = min(n, lo + clen);
+            w.g = v.tok[step & 1] + lo;  // lo is a multiple of 8 tokens: 16-byte aligned
+            if (threadIdx.x == 0) sm.chunk_n = (int)(hi - lo);
+            w.res_mode = w.fresh = true;
+            __syncthreads();
+        }
+    }
+    if (w.res_mode && !w.in_smem && sm.chunk_n <= kChunkCap) {
+        const int cn = sm.chunk_n;
+        const uint16_t *src = w.g;
+        for (int i = threadIdx.x * 8; i + 8 <= cn; i += kTPB * 8)
+            *reinterpret_cast<uint4 *>(chunk_smem + i) = *reinterpret_cast<const uint4 *>(src + i);
+        for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk_smem[i] = src[i];
+        w.in_smem = true;
+        __syncthreads();
+    }
+}
+
+// End of the run: back to one contiguous stream in tok[step & 1] (step = merges done), where the host expects it.
 template <class Grid>
-__device__ __forceinline__ void resident_write_back(Grid &grid, const TrainView &v, uint32_t step, int cn, const uint16_t *chunk) {
+__device__ __forceinline__ void resident_write_back(Grid &grid, const TrainView &v, uint32_t step, int cn, const uint16_t *chunk,
+                                                    bool from_start) {
     if (threadIdx.x == 0) v.cta_counts[blockIdx.x] = (uint32_t)cn;
     grid.sync();
     unsigned long long pre = 0, all = 0;
@@ -1105,8 +1154,19 @@ __device__ __forceinline__ void resident_write_back(Grid &grid, const TrainView 
     __syncthreads();
     pre = all = 0;
     for (int q = 0; q < kTPB / 32; q++) { pre += s_pre[q]; all += s_all[q]; }
-    uint16_t *dst = v.tok[step & 1] + pre;
+    // chunks that were formed before the first step may still live in buffer 0: gather in buffer 1 first
+    const uint32_t to = from_start ? 1u : (step & 1u);
+    uint16_t *dst = v.tok[to] + pre;
     for (int i = threadIdx.x; i < cn; i += kTPB) dst[i] = chunk[i];
+    if (to != (step & 1u)) {
+        grid.sync();
+        const uint16_t *src = v.tok[1];
+        uint16_t *fin = v.tok[0];
+        const unsigned long long gt = (unsigned long long)blockIdx.x * kTPB + threadIdx.x, gn = (unsigned long long)gridDim.x * kTPB;
+        for (unsigned long long i = gt * 8; i + 8 <= all; i += gn * 8)
+            *reinterpret_cast<uint4 *>(fin + i) = *reinterpret_cast<const uint4 *>(src + i);
+        for (unsigned long long i = (all & ~7ull) + gt; i < all; i += gn) fin[i] = src[i];
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) v.dev->n[step & 1] = all;
 }
 
@@ -1115,29 +1175,13 @@ __global__ void __launch_bounds__(kTPB, kCtasPerSm) train_loop_kernel(TrainView 
     __shared__ MergeSmem sm;
     __shared__ Best s_best;
     extern __shared__ __align__(16) uint16_t chunk[];  // kChunkCap tokens (resident tail)
-    bool res_mode = false, res_fresh = false;
+    ChunkWhere w;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     ECGB_MARK_DECL;
     uint32_t step = 0;
     for (; step < n_steps; step++) {
         ECGB_MARK_RESET;
-        if (!res_mode && v.resident_ok) {
-            // the stream now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
-            const unsigned long long n = v.dev->n[step & 1];
-            const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;
-            if (clen <= (unsigned long long)kChunkCap) {
-                const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
-                const unsigned long long hi = min(n, lo + clen);
-                const uint16_t *src = v.tok[step & 1] + lo;  // lo is a multiple of 8 tokens: 16-byte aligned
-                const int cn = (int)(hi - lo);
-                for (int i = threadIdx.x * 8; i + 8 <= cn; i += kTPB * 8)
-                    *reinterpret_cast<uint4 *>(chunk + i) = *reinterpret_cast<const uint4 *>(src + i);
-                for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk[i] = src[i];
-                if (threadIdx.x == 0) sm.chunk_n = cn;
-                res_mode = res_fresh = true;
-                __syncthreads();
-            }
-        }
+        chunk_step_begin(v, step, sm, chunk, w);
         const Best fin = grid_argmax(grid, v, &s_best);
         if (gtid == 0) {
             v.best[step] = fin;
@@ -1146,21 +1190,25 @@ __global__ void __launch_bounds__(kTPB, kCtasPerSm) train_loop_kernel(TrainView 
         if (fin.count == 0) break;  // no pair left (lib.rs:88-90); uniform over the grid
         if (threadIdx.x == 0) atomicAdd(v.arrive, 1u);  // this CTA no longer reads the histogram in this step
         ECGB_MARK(0);
-        if (res_mode) {
+        if (w.res_mode) {
             const bool xx = (fin.key >> 16) == (fin.key & 0xFFFFu);
-            if (xx || res_fresh) {  // otherwise the records published by the previous pass are all that is needed
-                if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, fin.key >> 16, xx, &v.cta_bd[(step & 1) * v.cta_stride + blockIdx.x]);
+            if (xx || w.fresh) {  // otherwise the records published by the previous pass are all that is needed
+                if (threadIdx.x < 32)
+                    chunk_boundary(w.in_smem ? chunk : w.g, sm.chunk_n, fin.key >> 16, xx, &v.cta_bd[(step & 1) * v.cta_stride + blockIdx.x]);
                 grid.sync();  // every chunk's boundary record is visible
             }
-            res_fresh = false;
+            w.fresh = false;
+            const Boundary *bd = v.cta_bd + (step & 1) * v.cta_stride;
+            if (w.in_smem) merge_pass<false, true>(v, step, fin, bd, v.main, sm, chunk);
+            else merge_pass<false, true>(v, step, fin, bd, v.main, sm, w.g);
+        } else {
+            merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr);
         }
-        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (step & 1) * v.cta_stride, v.main, sm, chunk);
-        else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr);
         ECGB_MARK_RESET;
         grid.sync();
         ECGB_MARK(10);
     }
-    if (res_mode) resident_write_back(grid, v, step, sm.chunk_n, chunk);
+    if (w.res_mode) resident_write_back(grid, v, step, sm.chunk_n, w.in_smem ? chunk : w.g, w.from_start);
 }
 
 // ------------------------------------------------------------------ persistent sharded loop
@@ -1255,7 +1303,7 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
                                                int &s_last, uint16_t *chunk) {
     AbortableGrid grid{v.gbar, v.abort, 0u};
     volatile unsigned int *abort = v.abort;
-    bool res_mode = false, res_fresh = false;
+    ChunkWhere w;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
     uint8_t *const mine = pv.area[pv.rank];
@@ -1264,23 +1312,7 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
     for (; step < n_steps; step++) {
         ECGB_MARK_RESET;
         if (*abort) break;
-        if (!res_mode && v.resident_ok) {
-            // the shard now fits in the CTAs' shared memory: load this CTA's chunk and stay on chip
-            const unsigned long long n = v.dev->n[step & 1];
-            const unsigned long long clen = (((n + gridDim.x - 1) / gridDim.x) + 7ull) & ~7ull;
-            if (clen <= (unsigned long long)kChunkCap) {
-                const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
-                const unsigned long long hi = min(n, lo + clen);
-                const uint16_t *src = v.tok[step & 1] + lo;
-                const int cn = (int)(hi - lo);
-                for (int i = threadIdx.x * 8; i + 8 <= cn; i += kTPB * 8)
-                    *reinterpret_cast<uint4 *>(chunk + i) = *reinterpret_cast<const uint4 *>(src + i);
-                for (int i = (cn & ~7) + threadIdx.x; i < cn; i += kTPB) chunk[i] = src[i];
-                if (threadIdx.x == 0) sm.chunk_n = cn;
-                res_mode = res_fresh = true;
-                __syncthreads();
-            }
-        }
+        chunk_step_begin(v, step, sm, chunk, w);
         const Best fin = grid_argmax(grid, v, &s_best);
         if (gtid == 0) {
             v.best[step] = fin;
@@ -1291,23 +1323,28 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
         const int par = (int)(step & 1u);
         const uint32_t a = fin.key >> 16;
         const bool xx = a == (fin.key & 0xFFFFu);
-        if (res_mode && (xx || res_fresh)) {
-            if (threadIdx.x < 32) chunk_boundary(chunk, sm.chunk_n, a, xx, &v.cta_bd[(size_t)par * v.cta_stride + blockIdx.x]);
+        if (w.res_mode && (xx || w.fresh)) {
+            if (threadIdx.x < 32) chunk_boundary(w.in_smem ? chunk : w.g, sm.chunk_n, a, xx, &v.cta_bd[(size_t)par * v.cta_stride + blockIdx.x]);
             grid.sync();
         }
-        res_fresh = false;
+        w.fresh = false;
         if (xx && blockIdx.x == 0 && threadIdx.x < 32) {
             // second exchange of an (x,x) step: the run fields of this shard's record
             uint32_t tp = 0, alla = 0;
-            shard_run_fields(v, step, res_mode, a, &tp, &alla);
+            shard_run_fields(v, step, w.res_mode, a, &tp, &alla);
             tp = __shfl_sync(0xffffffffu, tp, 0);
             alla = __shfl_sync(0xffffffffu, alla, 0);
             if ((int)threadIdx.x < pv.world && (int)threadIdx.x != pv.rank)  // lane r serves peer r
                 st_unit(pv.area[threadIdx.x] + peer_rec_off(pv.world, par, pv.rank) + 8 * 5, tp | (alla << 1), peer_tag(pv.epoch, step));
         }
         ECGB_MARK(0);
-        if (res_mode) merge_pass<false, true>(v, step, fin, v.cta_bd + (size_t)par * v.cta_stride, v.main, sm, chunk, &pv);
-        else merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr, &pv);
+        if (w.res_mode) {
+            const Boundary *bd = v.cta_bd + (size_t)par * v.cta_stride;
+            if (w.in_smem) merge_pass<false, true>(v, step, fin, bd, v.main, sm, chunk, &pv);
+            else merge_pass<false, true>(v, step, fin, bd, v.main, sm, w.g, &pv);
+        } else {
+            merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr, &pv);
+        }
         ECGB_MARK_RESET;
         // this CTA's patches are in the local table (device-scope fence: the last CTA to arrive reads the list
         // length and the chunk records) and on their way to the peers (self-validating, no fence)
@@ -1325,7 +1362,7 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
             __threadfence();
             Boundary *rec = &sm.bd_near[0];  // free between passes
             bool fast = false;
-            if (res_mode) {
+            if (w.res_mode) {
                 // usual case: the first chunk holds >= 3 tokens and the last one >= 2 -- both records in one round trip
                 const Boundary *cb = v.cta_bd + (size_t)(par ^ 1) * v.cta_stride;
                 const uint32_t val = ld_vol(reinterpret_cast<const uint32_t *>(lane < 16 ? &cb[0] : &cb[gridDim.x - 1]) + (lane & 15));
@@ -1343,7 +1380,7 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
                     reinterpret_cast<uint32_t *>(rec)[lane] = w;
                 }
             }
-            if (!fast && lane == 0) shard_record(v, step + 1u, res_mode, rec);
+            if (!fast && lane == 0) shard_record(v, step + 1u, w.res_mode, rec);
             __syncwarp();
             uint32_t cnt = ld_vol(pv.out_count + par);
             if (cnt > pv.cap) cnt = pv.cap;  // overflow was flagged by push_entry
@@ -1398,7 +1435,7 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
         grid.sync();
         ECGB_MARK(10);
     }
-    if (res_mode) resident_write_back(grid, v, step, sm.chunk_n, chunk);
+    if (w.res_mode) resident_write_back(grid, v, step, sm.chunk_n, w.in_smem ? chunk : w.g, w.from_start);
     if (gtid == 0) v.dev->cur_step = step;
 }
 
@@ -1760,7 +1797,7 @@ extern "C" int ecgb_trainer_run(ecgb_trainer *t, uint32_t num_merges, uint32_t *
         const char *knob = getenv("ECGB_REDUNDANT_ARGMAX");  // tuning knob (profiles/train_knobs.py)
         view.redundant_max = knob ? (uint32_t)atoi(knob) : kRedundantArgmax;
         knob = getenv("ECGB_RESIDENT_TAIL");
-        view.resident_ok = knob ? (uint32_t)atoi(knob) : 1u;
+        view.resident_ok = knob ? (uint32_t)atoi(knob) : 2u;
         uint32_t steps = num_merges;
         void *kargs[] = {&view, &steps};
         ECGB_CUDA(cudaLaunchCooperativeKernel((const void *)train_loop_kernel, dim3(grid), dim3(kTPB), kargs, dyn_smem, st));
@@ -2076,7 +2113,7 @@ static int dist_prepare(ecgb_trainer *t, int rank, int world, void *const *d_are
     TrainView view = t->v;
     view.redundant_max = kRedundantArgmax;
     const char *knob = getenv("ECGB_RESIDENT_TAIL");
-    view.resident_ok = knob ? (uint32_t)atoi(knob) : 1u;
+    view.resident_ok = knob ? (uint32_t)atoi(knob) : 2u;
     PeerView pv{};
     pv.rank = rank;
     pv.world = world;
