@@ -506,6 +506,7 @@ struct MergeSmem {
     Boundary bd_peer[kMaxWorld];  // persistent sharded loop: every rank's shard record for this step
     PeerPush push;             // persistent sharded loop: where this step's patches go
     uint32_t peer_cnt[kMaxWorld];  // persistent sharded loop: entries of each peer's patch list of this step
+    __align__(8) unsigned long long mbar[kChunkTiles];  // chunks in global memory: one mbarrier per slot of the tile ring
     // in[8 + q] = token at tile position q; in[6..7] / in[8 + kTile ..] = 2 / 3 tokens of context
     __align__(16) uint16_t in[kTile + 16];
     // kept tokens of the tile, compacted; 32-bit words XOR-swizzled (see stage_index)
@@ -580,10 +581,42 @@ __device__ __forceinline__ void st_unit(void *p, uint32_t payload, uint32_t tag)
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(peer_unit(payload, tag)) : "memory");
 }
 
-template <bool TICKETS, bool RESIDENT>
+// ---- tile ring of a chunk that lives in global memory: the bulk-copy engine (cp.async.bulk, "TMA" 1-D) streams
+// the CTA's next tiles into shared memory while the current one is merged; an mbarrier per slot counts the bytes.
+// Built only with -DECGB_TILE_RING: measured on B200 (1.2e9-symbol corpus, 2 000 merges) it is bit-exact but
+// SLOWER than the plain 128-bit loads (0.677 s vs 0.613 s) -- the pass is bound by its barriers and instruction
+// stream, not by load latency (ncu: barrier stalls 4.6 of 10 warp-cycles, issue 55 %), so prefetching buys nothing.
+struct TileRing {
+    uint16_t *slots;        // kChunkTiles x kTile tokens (the dynamic shared memory the resident chunk uses later)
+    uint32_t uses[kChunkTiles];  // copies issued into each slot so far (parity of the phase to wait for); same in every thread
+};
+__device__ __forceinline__ void ring_init(MergeSmem &sm) {  // one thread, once per kernel
+#pragma unroll
+    for (int s = 0; s < kChunkTiles; s++)
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.mbar[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ring_issue(MergeSmem &sm, const TileRing &ring, int slot, const uint16_t *src, uint32_t bytes) {  // one thread
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.mbar[slot]);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring.slots + (size_t)slot * kTile);
+    asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ring_wait(MergeSmem &sm, int slot, uint32_t parity) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.mbar[slot]);
+    uint32_t ok = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <bool TICKETS, bool RESIDENT, bool RING = false>
 __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, const Best bb,
                                            const Boundary *__restrict__ all_bd, const PairTable &upd, MergeSmem &sm,
-                                           uint16_t *chunk, const PeerView *pv = nullptr) {
+                                           uint16_t *chunk, const PeerView *pv = nullptr, TileRing *ring = nullptr) {
+    static_assert(!RING || RESIDENT, "the tile ring feeds chunks");
     // Resident tail (chunk != nullptr, cooperative kernel only): the stream lives in the CTAs' shared
     // memory, one contiguous chunk each, and is merged in place; the chunks are shards exactly like the
     // ranks of a sharded run (all_bd = every CTA's boundary record), so no output offsets are needed.
@@ -682,6 +715,20 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         return q < (long long)h.nr ? h.R[q] : kSentinel;
     };
 
+    // RING: tile t of the chunk goes through slot t % kChunkTiles; two tiles are in flight ahead of the merge
+    auto tile_bytes = [&](long long t) -> uint32_t {
+        const long long valid = min((long long)kTile, n - t * kTile);
+        return (uint32_t)((valid * 2 + 15) & ~15ll);  // the token buffers end with slack, chunk starts are 16-byte aligned
+    };
+    uint32_t ring_used[kChunkTiles] = {0, 0, 0};  // copies issued in this pass, per slot
+    if (RING) {
+        if (threadIdx.x == 0 && n > 0) {
+            ring_issue(sm, *ring, 0, in, tile_bytes(0));
+            if (ntiles > 1) ring_issue(sm, *ring, 1, in + kTile, tile_bytes(1));
+        }
+        if (n > 0) { ring_used[0]++; if (ntiles > 1) ring_used[1]++; }
+    }
+
     unsigned long long chunk_fill = 0;  // resident: tokens of the chunk written so far
     for (long long round = 0;; round++) {
         long long tile;
@@ -701,11 +748,28 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         const int nvalid = min(kIPT, max(0, tile_valid - (int)threadIdx.x * kIPT));  // ... in this thread's range
         const uint32_t validmask = (1u << nvalid) - 1u;
 
+        const uint16_t *next_slot = nullptr;  // RING: the tile after this one, already in shared memory
+        if (RING && n > 0) {
+            const int slot = (int)(tile % kChunkTiles);
+            // the slot of tile + 2 held tile - 1, which every thread finished reading before the barrier above
+            if (tile + 2 < ntiles) {
+                const int s2 = (int)((tile + 2) % kChunkTiles);
+                if (threadIdx.x == 0) ring_issue(sm, *ring, s2, in + (tile + 2) * kTile, tile_bytes(tile + 2));
+                ring_used[s2]++;
+            }
+            ring_wait(sm, slot, (ring->uses[slot] + ring_used[slot] - 1u) & 1u);
+            if (tile + 1 < ntiles) {
+                const int s1 = (int)((tile + 1) % kChunkTiles);
+                ring_wait(sm, s1, (ring->uses[s1] + ring_used[s1] - 1u) & 1u);
+                next_slot = ring->slots + (size_t)s1 * kTile;
+            }
+        }
         // ---- 16 tokens per thread, two per 32-bit word (token 2j = low half of w[j]) ----
         uint32_t w[kIPT / 2];
         if (nvalid == kIPT) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(in + base);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(in + base + 8);
+            const uint16_t *src16 = RING ? ring->slots + (size_t)(tile % kChunkTiles) * kTile + threadIdx.x * kIPT : in + base;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(src16);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(src16 + 8);
             w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
             w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
         } else {  // end of the shard: positions >= n show the right halo (or the sentinel)
@@ -720,7 +784,10 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
         // (resident: the tokens before this tile have already been merged in place; the previous tile left a copy)
         if (threadIdx.x < 2)
             sm.in[6 + threadIdx.x] = (uint16_t)((resident && tile > 0) ? sm.carry_ctx[threadIdx.x] : tok_at(tbase - 2 + threadIdx.x));
-        if (threadIdx.x >= 2 && threadIdx.x < 5) sm.in[8 + kTile + threadIdx.x - 2] = (uint16_t)tok_at(tbase + kTile + threadIdx.x - 2);
+        if (threadIdx.x >= 2 && threadIdx.x < 5) {
+            const long long pr = tbase + kTile + threadIdx.x - 2;  // right context: the first tokens of the next tile
+            sm.in[8 + kTile + threadIdx.x - 2] = (uint16_t)((RING && next_slot != nullptr && pr < n) ? next_slot[threadIdx.x - 2] : tok_at(pr));
+        }
         __syncthreads();
         ECGB_MARK(2);
         if (resident && threadIdx.x == kTPB - 1) { sm.carry_ctx[0] = w[7] & 0xFFFFu; sm.carry_ctx[1] = w[7] >> 16; }
@@ -929,6 +996,12 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             out[gofs + tile_total - 1] = stage16[stage_index((uint32_t)tile_total - 1u)];
         ECGB_MARK(8);
     }
+    if (RING) {
+#pragma unroll
+        for (int q = 0; q < kChunkTiles; q++) ring->uses[q] += ring_used[q];
+        // the next pass reads this chunk through the bulk-copy engine (async proxy): order this thread's stores before it
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
     if (resident) {
         __syncthreads();  // the chunk is complete
         // record for the next step (other parity: slower CTAs may still be reading this step's records);
@@ -1096,6 +1169,7 @@ struct ChunkWhere {
     bool in_smem = false;    // this CTA's chunk is in shared memory
     bool fresh = false;      // chunks were just formed: no boundary records published yet
     bool from_start = false; // resident_ok = 2
+    TileRing ring;           // tile ring of a chunk in global memory
 };
 
 __device__ __forceinline__ void chunk_step_begin(const TrainView &v, uint32_t step, MergeSmem &sm, uint16_t *chunk_smem, ChunkWhere &w) {
@@ -1105,7 +1179,12 @@ __device__ __forceinline__ void chunk_step_begin(const TrainView &v, uint32_t st
         const unsigned long long lo = min(n, (unsigned long long)blockIdx.x * clen);
         const unsigned long long hi = min(n, lo + clen);
         w.g = v.tok[0] + lo;
-        if (threadIdx.x == 0) sm.chunk_n = (int)(hi - lo);
+        if (threadIdx.x == 0) {
+            sm.chunk_n = (int)(hi - lo);
+            ring_init(sm);
+        }
+        w.ring.slots = chunk_smem;
+        w.ring.uses[0] = w.ring.uses[1] = w.ring.uses[2] = 0;
         w.res_mode = w.fresh = w.from_start = true;
         __syncthreads();
     } else if (!w.res_mode && v.resident_ok == 1u) {
@@ -1200,6 +1279,9 @@ __global__ void __launch_bounds__(kTPB, kCtasPerSm) train_loop_kernel(TrainView 
             w.fresh = false;
             const Boundary *bd = v.cta_bd + (step & 1) * v.cta_stride;
             if (w.in_smem) merge_pass<false, true>(v, step, fin, bd, v.main, sm, chunk);
+#ifdef ECGB_TILE_RING
+            else if (w.from_start) merge_pass<false, true, true>(v, step, fin, bd, v.main, sm, w.g, nullptr, &w.ring);
+#endif
             else merge_pass<false, true>(v, step, fin, bd, v.main, sm, w.g);
         } else {
             merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr);
@@ -1341,6 +1423,9 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
         if (w.res_mode) {
             const Boundary *bd = v.cta_bd + (size_t)par * v.cta_stride;
             if (w.in_smem) merge_pass<false, true>(v, step, fin, bd, v.main, sm, chunk, &pv);
+#ifdef ECGB_TILE_RING
+            else if (w.from_start) merge_pass<false, true, true>(v, step, fin, bd, v.main, sm, w.g, &pv, &w.ring);
+#endif
             else merge_pass<false, true>(v, step, fin, bd, v.main, sm, w.g, &pv);
         } else {
             merge_pass<false, false>(v, step, fin, nullptr, v.main, sm, nullptr, &pv);
