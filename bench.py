@@ -30,9 +30,19 @@ import numpy as np  # noqa: E402
 C_LEADS, L_SAMPLES = 12, 5000
 REC_LEN = C_LEADS * L_SAMPLES
 FIXTURE = os.path.join(ROOT, "tests", "golden", "ptbxl_1000_m5000.npz")
+FIXTURE_10K = os.path.join(ROOT, "tests", "golden", "ptbxl_1000_m10000.npz")
 WORKLOAD = "encode-only: 100k synthetic PTB-XL-shaped records (12x5000 fp32) per GPU, fixed 5000-merge table"
 METRIC = "ECG records tokenized/sec"
 UNIT = "records/s"
+
+
+def bench_config(args, n_merges):
+    """The `config` object of the JSON line -- the same keys and values in both arms (the reference arm times a
+    bounded sample of this workload and says so in cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "records_per_gpu": int(args.records), "leads": C_LEADS, "samples_per_lead": L_SAMPLES,
+            "input_dtype": "fp32", "n_merges": int(n_merges), "table": "tests/golden/ptbxl_1000_m5000.npz (config-1 corpus)",
+            "parallelism": "records sharded x%d, no data-path collective" % int(args.gpus),
+            "l2": "inputs (%.1f GB/GPU) exceed L2; no flush" % (args.records * REC_LEN * 4 / 1e9)}
 
 
 def load_table():
@@ -147,13 +157,22 @@ def run_reference(args, rank, world):
         t_tot += dt
         n_tot += per_step
     value = n_tot / t_tot
+    # the reference's own NumPy front half as it executes it (np.vectorize, ''.join), one core
+    from oracle import py_restatement as P
+    t0 = time.perf_counter()
+    n_np = 0
+    while time.perf_counter() - t0 < 2.0:
+        P.normalize_all_as_written(cal[n_np % len(cal)].astype(np.float64), pct["percentile_1"], pct["percentile_99"])
+        n_np += 1
+    numpy_rate = n_np / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "records_per_step": per_step, "input": "fp32 12x5000", "n_merges": len(pairs)},
+        "config": bench_config(args, len(pairs)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d records/step x %d steps, trie rebuilt per record as rust_bpe.encode_text does" % (per_step, args.steps)},
+                         "sample": "%d records/step x %d steps, trie rebuilt per record as rust_bpe.encode_text does" % (per_step, args.steps),
+                         "numpy_as_written_records_per_s_per_core": numpy_rate},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -161,20 +180,69 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------- CUDA arm
+def bind_to_gpu_numa(dev):
+    """CPU affinity of this rank -> the cores next to its GPU, so that the pinned buffers allocated afterwards
+    (first touch) and the copy-issuing thread sit on the GPU's NUMA node.  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus of %s" % (len(cpus), bdf)
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
+
+
+def progress(msg):
+    """stage marker on stderr (rank 0): the JSON line on stdout stays alone"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
+def timed(fn, reps, dev, torch):
+    """mean milliseconds of fn() over reps calls, CUDA events on the current stream"""
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    e[0].record()
+    for i in range(reps):
+        fn()
+        e[i + 1].record()
+    torch.cuda.synchronize(dev)
+    return [e[i].elapsed_time(e[i + 1]) for i in range(reps)]
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from ecgbyte import synth
-    from ecgbyte.api import EncodePipeline, Quantizer, Vocab
+    from ecgbyte.api import EncodePipeline, EncodePipelineCSR, Quantizer, Vocab
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(dev)
     pairs, pct = load_table()
     n_rec = args.records
     stride = args.out_stride
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
     q = Quantizer(pct, dtype=torch.float32, device=dev)
     v = Vocab.from_pairs(pairs, device=dev)
@@ -188,6 +256,22 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(vals):
+        if world == 1:
+            return [float(a) for a in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(a) for a in t]
+
+    def allsum(vals):
+        if world == 1:
+            return [float(a) for a in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return [float(a) for a in t]
+
+    progress("batch generated; timing the fused encode kernel")
+    # ---- headline: the fused quantise+encode kernel over the resident batch ----
     for _ in range(max(args.warmup, 3)):
         v.encode_batch(q, x, out_stride=stride, tokens=tokens, lens=lens)
     barrier()
@@ -208,73 +292,131 @@ def run_ours(args, rank, world, local_rank):
     assert lens_h.max() <= stride, "out_stride %d too small (max tokens %d)" % (stride, lens_h.max())
     total_tokens = int(lens_h.sum())
 
-    # ---- e2e: host buffers through the public host API (H2D + kernel + D2H every step) ----
+    progress("encode timed; quantize_kernel alone")
+    # ---- K1 alone: ecgb_quantize over the same batch (C*L*(e+1) bytes per record) ----
+    sym_out = torch.empty((n_rec, REC_LEN), dtype=torch.uint8, device=dev)
+    q.quantize(x, out=sym_out)
+    barrier()
+    k1_ms = float(np.mean(timed(lambda: q.quantize(x, out=sym_out), 5, dev, torch)))
+    k1_bytes = n_rec * REC_LEN * (4 + 1)
+    # spot check of K1 on the timed batch
+    from oracle import oracle as O
+    k1_idx = [0, n_rec // 2, n_rec - 1]
+    k1_ok = all(np.array_equal(sym_out[r].cpu().numpy(),
+                               O.quantize(x[r].cpu().numpy(), pct["percentile_1"], pct["percentile_99"]).reshape(-1)) for r in k1_idx)
+    del sym_out
+    if not k1_ok:
+        raise SystemExit("bench.py: PARITY FAILURE (quantize_kernel differs from the oracle) -- numbers withheld")
+
+    progress("end-to-end pipelines (host buffers)")
+    # ---- e2e: host buffers through the public host API (H2D + kernels + D2H every step) ----
     n_e2e = min(args.e2e_records, n_rec)
     xh = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.float32).pin_memory()
     xh.copy_(x[:n_e2e])
-    tok_h = torch.empty((n_e2e, stride), dtype=torch.int32).pin_memory()
+    tok16_h = torch.empty((n_e2e * 6144,), dtype=torch.uint16).pin_memory()
     len_h = torch.empty((n_e2e,), dtype=torch.int32).pin_memory()
-    pipe = EncodePipeline(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
-    for _ in range(2):
-        pipe.run(xh, tok_h, len_h)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pipe = EncodePipelineCSR(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
     e2e_steps = max(3, min(args.steps, 5))
-    e0.record()
-    launches_e2e = 0
-    for _ in range(e2e_steps):
-        launches_e2e += pipe.run(xh, tok_h, len_h)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    assert np.array_equal(len_h.numpy(), lens_h[:n_e2e].astype(np.int32)), "e2e lengths differ from device-resident run"
 
-    # informational: the same pipeline fed with int16 records (1 uV/LSB, PTB-XL's native type):
-    # half the PCIe bytes per record
-    e2e_i16 = None
+    def time_pipe(p, xin, tok_out):
+        for _ in range(2):
+            p.run(xin, tok_out, len_h)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_l, n_t = 0, 0
+        for _ in range(e2e_steps):
+            r = p.run(xin, tok_out, len_h)
+            n_l += r[0] if isinstance(r, tuple) else r
+            n_t = r[1] if isinstance(r, tuple) else 0
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n_l, n_t
+
+    e2e_ms, launches_e2e, e2e_tokens = time_pipe(pipe, xh, tok16_h)
+    assert np.array_equal(len_h.numpy(), lens_h[:n_e2e].astype(np.int32)), "e2e lengths differ from device-resident run"
+    e2e_tok_copy = tok16_h[:e2e_tokens].numpy().copy()
+    e2e_off = np.concatenate([[0], np.cumsum(lens_h[:n_e2e])])
+
+    # the same pipeline fed with int16 records (1 uV/LSB, PTB-XL's native storage type): half the PCIe bytes per record
+    e2e_i16_ms = None
     if not args.no_i16:
         q16 = Quantizer(pct, dtype=torch.int16, device=dev)
         x16 = torch.clamp(torch.round(x[:n_e2e] * 1000.0), -32768, 32767).to(torch.int16)
         xh16 = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.int16).pin_memory()
         xh16.copy_(x16)
-        pipe16 = EncodePipeline(v, q16, REC_LEN, stride, chunk=args.e2e_chunk)
-        pipe16.run(xh16, tok_h, len_h)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(e2e_steps):
-            pipe16.run(xh16, tok_h, len_h)
-        f1.record()
-        barrier()
-        e2e_i16 = n_e2e * e2e_steps / (f0.elapsed_time(f1) * 1e-3)
-        del x16, xh16, pipe16
-        # restore the fp32 results in the pinned buffers for the parity gate below
-        pipe.run(xh, tok_h, len_h)
-        torch.cuda.synchronize(dev)
+        pipe16 = EncodePipelineCSR(v, q16, REC_LEN, stride, chunk=args.e2e_chunk)
+        e2e_i16_ms, _, i16_tokens = time_pipe(pipe16, xh16, tok16_h)
+        del x16, pipe16
 
-    # ---- max over ranks ----
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-        tt = torch.tensor([total_tokens], dtype=torch.int64, device=dev)
-        dist.all_reduce(tt)
-        total_tokens_all = int(tt[0])
-    else:
-        total_tokens_all = total_tokens
-    train_dist = None
-    if world > 1 and not args.no_train:
-        train_dist = bench_train_sharded(dev, pct, rank, world)
+    # padded int32 rows (round-1 output format), for comparison
+    tok32_h = torch.empty((n_e2e, stride), dtype=torch.int32).pin_memory()
+    pipe32 = EncodePipeline(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
+    e2e32_ms, _, _ = time_pipe(pipe32, xh, tok32_h)
+    del pipe32
+
+    progress("bare copy ceiling")
+    # ---- bare pinned-copy ceiling of this box at `world` concurrent ranks: the same bytes, no kernels ----
+    d_buf = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copies(h2d, d2h):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if h2d:
+                with torch.cuda.stream(s_in):
+                    d_buf.copy_(xh, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s_out):
+                    tok32_h.copy_(tokens[:n_e2e], non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+        return (time.perf_counter() - t0) / 3
+
+    copies(True, True)
+    t_h2d = copies(True, False)
+    t_d2h = copies(False, True)
+    t_both = copies(True, True)
+    h2d_gbs = n_e2e * REC_LEN * 4 / t_h2d / 1e9
+    d2h_gbs = n_e2e * stride * 4 / t_d2h / 1e9
+    del d_buf, tok32_h
+
+    # ---- max / sum over ranks ----
+    total_ms, e2e_ms, e2e32_ms, k1_ms_max, t_h2d_max = allmax([total_ms, e2e_ms, e2e32_ms, k1_ms, t_h2d])
+    if e2e_i16_ms is not None:
+        e2e_i16_ms = allmax([e2e_i16_ms])[0]
+    total_tokens_all, e2e_tokens_all, h2d_sum, d2h_sum = allsum([total_tokens, e2e_tokens, h2d_gbs, d2h_gbs])
+
+    progress("config 3")
+    # ---- config 3: the 10,000-merge table (does not fit in shared memory next to the walkers' rings) ----
+    cfg3 = None
+    if not args.no_config3:
+        cfg3 = bench_config3(args, dev, rank, world, x, q, pct, peak, barrier, allmax)
+
+    del x, tokens
+    torch.cuda.empty_cache()
+
+    progress("training")
+    # ---- BPE training: config 1 and config 4 ----
+    train = None
+    if not args.no_train:
+        train = bench_train(args, dev, pct, peak, rank, world)
+
     if rank != 0:
         return
 
     value = world * n_rec * args.steps / (total_ms * 1e-3)
     e2e_value = world * n_e2e * e2e_steps / (e2e_ms * 1e-3)
 
+    progress("parity gate")
     # ---- parity gate: a sample of the timed batch against the CPU oracle ----
-    from oracle import oracle as O
+    x = synth.corpus_cuda(2024, n_rec, L_SAMPLES, torch.float32, dev, start=rank * n_rec)
+    tokens = torch.empty((n_rec, stride), dtype=torch.int32, device=dev)
+    v.encode_batch(q, x, out_stride=stride, tokens=tokens, lens=lens)
     rng = np.random.default_rng(0)
-    idx = np.sort(rng.choice(n_rec, size=min(args.check, n_rec), replace=False))
+    idx = np.sort(np.concatenate([np.arange(min(8, n_rec)), rng.choice(n_rec, size=min(args.check, n_rec), replace=False)]))
+    idx = np.unique(idx)
     xs = x[torch.from_numpy(idx).to(dev)].cpu().numpy()
     sym = O.quantize(xs, pct["percentile_1"], pct["percentile_99"]).reshape(len(idx), -1)
     seq, off = O.expand(pairs)
@@ -287,34 +429,31 @@ def run_ours(args, rank, world, local_rank):
     for k in range(len(idx)):
         if not np.array_equal(g_tok[k, : w_len[k]], w_tok[k, : w_len[k]].astype(np.int32)):
             bad.append("tokens of record %d" % idx[k])
-    d4 = tokens[:4].cpu().numpy()
-    for k in range(4):  # the host-buffer path returns the same tokens as the resident path
-        if not np.array_equal(tok_h[k, : lens_h[k]].numpy(), d4[k, : lens_h[k]]):
+    for k in range(min(8, n_e2e)):  # the host-buffer path (compact 2-byte output) returns the same tokens
+        if not np.array_equal(e2e_tok_copy[e2e_off[k]:e2e_off[k + 1]].astype(np.int32), g_tok[k, : lens_h[k]]):
             bad.append("e2e tokens of record %d" % k)
     if bad:
         raise SystemExit("bench.py: PARITY FAILURE against the oracle (%s) -- numbers withheld" % ", ".join(bad[:5]))
 
     # ---- roofline of the (single) kernel of a step ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = n_rec * (REC_LEN * 4 + 4) + 4 * total_tokens          # C*L*e + 4T + 4 per record
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "encode_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic = tj["dram_bytes_per_record"] * n_rec
-        except Exception:
+            traffic_src = "profiles/encode_traffic.json (ncu --set full, commit %s)" % tj.get("commit", "?")
+        except Exception:  # noqa: BLE001
             traffic = None
 
+    progress("CPU baseline")
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu:
+        from oracle import py_restatement as P
         cores = os.cpu_count() or 1
         # calibrate on a few records, then time ~12 s of CPU work on records of the same batch
         cal_rate, _, _ = cpu_encode_rate(x[: 4 * cores].cpu().numpy(), pct, pairs, cores, faithful=True)
@@ -322,105 +461,262 @@ def run_ours(args, rank, world, local_rank):
         xs_cpu = x[:n_cpu].cpu().numpy()
         rate, dt, _ = cpu_encode_rate(xs_cpu, pct, pairs, cores, faithful=True)
         rate_am, dt_am, _ = cpu_encode_rate(xs_cpu[: max(n_cpu // 4, 4 * cores)], pct, pairs, cores, faithful=False)
+        # the reference's NumPy front half exactly as it executes it (np.vectorize + ''.join), one core, ~3 s
+        t0 = time.perf_counter()
+        n_np = 0
+        while time.perf_counter() - t0 < 3.0:
+            P.normalize_all_as_written(xs_cpu[n_np % n_cpu].astype(np.float64), pct["percentile_1"], pct["percentile_99"])
+            n_np += 1
+        np_rate = n_np / (time.perf_counter() - t0)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d records of the same batch in %.1f s; C port of normalize_all + rust_bpe.encode_text "
                          "(trie rebuilt per record as lib.rs:153-161 does); trie built once: %.0f records/s"
-                         % (n_cpu, dt, rate_am)}
+                         % (n_cpu, dt, rate_am),
+               "numpy_as_written": {"value": np_rate, "unit": "records/s per core", "records": n_np,
+                                    "what": "normalize_all + ''.join exactly as tokenizer_utils.py:14-19,59 execute them "
+                                            "(np.vectorize lambda per sample), float64 records, BEFORE encode_text is called; "
+                                            "x cores if fanned out like tokenizer_utils.py:89-91: %.0f records/s" % (np_rate * cores)}}
 
-    # ---- secondary metric: BPE-train merges/s (BASELINE.json config 1 scale), single GPU ----
-    train = None
-    if world == 1 and not args.no_train:
-        train = bench_train(dev, pct, peak)
-
+    rec_in_bytes, rec_out_bytes = REC_LEN * 4, 2.0 * e2e_tokens_all / (world * n_e2e) + 4
+    ceiling = h2d_sum * 1e9 / rec_in_bytes  # records/s if nothing but the input copy existed (the output copy runs the other way)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "records_per_gpu": n_rec, "leads": C_LEADS, "samples_per_lead": L_SAMPLES,
-                   "input_dtype": "fp32", "n_merges": int(len(pairs)), "out_stride": stride,
-                   "arithmetic": "fp32 threshold classification, bit-identical to the reference's float64 expression; "
-                                 "u8 symbols, 8-byte trie nodes, int32 tokens",
-                   "tokens_per_record": total_tokens_all / (world * n_rec), "parallelism": "records sharded x%d" % world,
-                   "l2": "inputs (%.1f GB/GPU) exceed L2; no flush" % (n_rec * REC_LEN * 4 / 1e9)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n_e2e * REC_LEN * 4,
-                "d2h_bytes_per_step": world * n_e2e * (stride * 4 + 4), "records_per_step": world * n_e2e, "steps": e2e_steps,
-                "api": "ecgbyte.api.EncodePipeline.run (pinned host in/out)",
-                "int16_input_records_per_s_per_gpu": e2e_i16},
+        "config": bench_config(args, len(pairs)),
+        "notes": {"arithmetic": "fp32 threshold classification, bit-identical to the reference's float64 expression; "
+                                "u8 symbols, 8-byte trie nodes, int32 tokens",
+                  "tokens_per_record": total_tokens_all / (world * n_rec), "out_stride": stride, "host_numa": numa},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n_e2e * rec_in_bytes),
+                "d2h_bytes_per_step": int(2 * e2e_tokens_all + 4 * world * n_e2e), "records_per_step": world * n_e2e, "steps": e2e_steps,
+                "api": "ecgbyte.api.EncodePipelineCSR.run (pinned host records in; pinned host 2-byte token ids, rows back to back, "
+                       "+ int32 lengths out; exact-size copies)",
+                "copy_ceiling": {"h2d_gbs_all_ranks": h2d_sum, "d2h_gbs_all_ranks": d2h_sum,
+                                 "h2d_plus_d2h_concurrent_s": t_both, "records_per_s": ceiling,
+                                 "what": "bare pinned cudaMemcpyAsync of the same buffers on %d rank(s) at once, no kernels" % world},
+                "frac_of_copy_ceiling": e2e_value / ceiling,
+                "padded_int32_rows_records_per_s": world * n_e2e * e2e_steps / (e2e32_ms * 1e-3)},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "ecgb::encode_kernel<F32>", "kernel_ms": k_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "ecgb::encode_kernel<F32>",
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+        "quantize": {"kernel": "ecgb::quantize_kernel<F32>", "ms": k1_ms_max, "records_per_s": world * n_rec / (k1_ms_max * 1e-3),
+                     "algorithmic_bytes_per_launch": k1_bytes, "achieved_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9,
+                     "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "parity": "3 records == oracle"},
         "cpu_baseline": cpu,
-        "train": train if train is not None else train_dist,
+        "config3": cfg3,
+        "train": train,
         "clocks": clocks,
         "parity": {"records_checked": int(len(idx)), "ok": True},
     }
+    if e2e_i16_ms is not None:
+        i16_value = world * n_e2e * e2e_steps / (e2e_i16_ms * 1e-3)
+        line["e2e_int16"] = {"value": i16_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n_e2e * REC_LEN * 2),
+                             "d2h_bytes_per_step": int(2 * e2e_tokens_all + 4 * world * n_e2e),
+                             "what": "the same pipeline fed int16 records (1 uV/LSB, PTB-XL's storage type)",
+                             "frac_of_copy_ceiling": i16_value / (h2d_sum * 1e9 / (REC_LEN * 2))}
     print(json.dumps(line), flush=True)
 
 
-def bench_train(dev, pct, peak):
-    """byte_pair_encoding on the config-1 corpus shape: 1,000 records = 6e7 symbols,
-    5,000 merges, whole loop on the device; checked against the oracle's merge list."""
+def bench_config3(args, dev, rank, world, x, q, pct, peak, barrier, allmax):
+    """BASELINE config 3: encode against a 10,000-merge table, a 1M-record corpus sharded over the GPUs.  The table is
+    trained here by the GPU trainer on the config-1 corpus and must equal the oracle's (fixture); each rank's share of
+    the 1M records is covered by repeated passes over its resident 100k-record batch."""
     import torch
     from ecgbyte import synth
-    from ecgbyte.api import Quantizer, Trainer
-    f = np.load(FIXTURE)
-    x = torch.from_numpy(synth.corpus(0, 1000, L_SAMPLES, np.float32)).to(dev)
-    q = Quantizer(pct, dtype=torch.float32, device=dev)
-    sym = q.quantize(x).reshape(-1)
-    m = 5000
-    tr = Trainer(sym.numel(), m, device=dev)
-    best = None
+    from ecgbyte.api import Quantizer, Trainer, Vocab
+    from oracle import oracle as O
+    f = np.load(FIXTURE_10K)
+    want = f["pairs"].astype(np.uint32)
+    xc = torch.from_numpy(synth.corpus(0, 1000, L_SAMPLES, np.float32)).to(dev)
+    symc = q.quantize(xc).reshape(-1)
+    tr = Trainer(symc.numel(), len(want), device=dev)
+    tr.load(symc)
+    t0 = time.perf_counter()
+    pairs10, counts10, _ = tr.run(len(want))
+    t_train = time.perf_counter() - t0
+    del tr, xc, symc
+    if not (np.array_equal(pairs10, want) and np.array_equal(counts10, f["counts"])):
+        raise SystemExit("bench.py: PARITY FAILURE (10,000-merge table differs from the oracle fixture)")
+    v10 = Vocab.from_pairs(pairs10, device=dev)
+    n_rec = x.shape[0]
+    stride = args.out_stride
+    tokens = torch.empty((n_rec, stride), dtype=torch.int32, device=dev)
+    lens = torch.empty((n_rec,), dtype=torch.int32, device=dev)
+    share = (1000000 + world - 1) // world
+    passes = max(1, (share + n_rec - 1) // n_rec)
     for _ in range(3):
-        tr.load(sym)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        pairs, counts, ntied = tr.run(m)  # synchronises at the end
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    ok = bool(np.array_equal(pairs, f["pairs"].astype(np.uint32)) and np.array_equal(counts, f["counts"]))
-    if not ok:
-        raise SystemExit("bench.py: PARITY FAILURE (merge list differs from the oracle fixture)")
-    n = tr.lengths(m).astype(np.float64)
-    alg = float(np.sum(2.0 * (n[:-1] + n[1:])))  # SURVEY.md 8d: 2*(n_t + n_{t+1}) bytes per step
-    return {"metric": "BPE-train merges/sec", "value": m / best, "unit": "merges/s", "seconds": best,
-            "corpus_symbols": int(n[0]), "merges": m, "final_tokens": int(n[-1]),
-            "algorithmic_bytes": alg, "achieved_gbs": alg / best / 1e9, "frac_of_hbm_peak": alg / best / 1e9 / peak,
-            "gpu_launches": 2, "parity": "merge list == oracle fixture (5000 merges)"}
+        v10.encode_batch(q, x, out_stride=stride, tokens=tokens, lens=lens)
+    barrier()
+    ms = timed(lambda: v10.encode_batch(q, x, out_stride=stride, tokens=tokens, lens=lens), passes, dev, torch)
+    barrier()
+    tot_ms = allmax([float(np.sum(ms))])[0]
+    T = int(lens.sum().item())
+    out = None
+    if rank == 0:
+        idx = np.array([0, n_rec // 3, n_rec - 1])
+        xs = x[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        sym = O.quantize(xs, pct["percentile_1"], pct["percentile_99"]).reshape(len(idx), -1)
+        seq, off = O.expand(pairs10)
+        trie = O.Trie(flat=(seq, off, np.arange(256, 256 + len(pairs10), dtype=np.uint32)))
+        w_tok, w_len = trie.encode_batch(sym, stride)
+        g_tok = tokens[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        g_len = lens.cpu().numpy()[idx]
+        ok = np.array_equal(w_len.astype(np.int64), g_len.astype(np.int64)) and all(
+            np.array_equal(g_tok[k, : w_len[k]], w_tok[k, : w_len[k]].astype(np.int32)) for k in range(len(idx)))
+        if not ok:
+            raise SystemExit("bench.py: PARITY FAILURE (config 3 tokens differ from the oracle)")
+        alg = n_rec * (REC_LEN * 4 + 4) + 4 * T
+        k_ms = float(np.mean(ms))
+        out = {"workload": "encode-only: 1M synthetic records (12x5000 fp32) sharded over %d GPU(s), 10,000-merge table" % world,
+               "value": world * passes * n_rec / (tot_ms * 1e-3), "unit": UNIT, "records": world * passes * n_rec,
+               "passes_over_resident_batch": passes, "records_per_gpu_resident": n_rec, "ms_per_pass": k_ms,
+               "tokens_per_record": T / n_rec, "table": dict(v10.info()),
+               "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (k_ms * 1e-3) / 1e9 / peak},
+               "table_training": {"merges": int(len(pairs10)), "seconds": t_train, "parity": "merge list == oracle fixture (10000 merges)"},
+               "parity": "3 records == oracle"}
+    del tokens, lens, v10
+    return out
 
 
-def bench_train_sharded(dev, pct, rank, world):
-    """The same corpus cut into `world` contiguous shards, one per rank; two NCCL all-gathers
-    per merge step (ecgbyte/dist_train.py).  Rank 0 checks the merge list against the fixture."""
+def bench_train(args, dev, pct, peak, rank, world):
+    """BPE-train merges/s.  Config 1 (1,000 records = 6e7 symbols, 5,000 merges): one GPU runs train_loop_kernel; N GPUs
+    run dist_loop_kernel on N contiguous shards (device-initiated exchange over NVLink), and the `auto` policy
+    (corpus fits one GPU -> do not shard) is reported beside it.  Config 4 (250k records = 1.5e10 symbols, 20,000
+    merges) at the same N.  Merge lists are checked against the oracle fixture (config 1) and, for config 4, on a
+    CPU-holdable sub-corpus; the config-4 merge list's CRC is printed so that runs at different N can be compared."""
     import torch
     import torch.distributed as dist
     from ecgbyte import synth
-    from ecgbyte.api import Quantizer
-    from ecgbyte.dist_train import split_contiguous, train_shard
+    from ecgbyte.api import Quantizer, Trainer
+    from ecgbyte.dist_train import ShardedTrainer, split_contiguous
+    from oracle import oracle as O
     f = np.load(FIXTURE)
-    x = torch.from_numpy(synth.corpus(0, 1000, L_SAMPLES, np.float32)).to(dev)
     q = Quantizer(pct, dtype=torch.float32, device=dev)
-    sym = q.quantize(x).reshape(-1)
-    lo, hi = split_contiguous(sym.numel(), world)[rank]
-    shard = sym[lo:hi].contiguous()
-    m = 5000
-    best = None
-    for _ in range(2):
+    out = {}
+
+    def crc(p):
+        p = np.asarray(p, np.uint64).reshape(-1)
+        return int(np.bitwise_xor.reduce(p * (np.arange(1, len(p) + 1, dtype=np.uint64) * np.uint64(2654435761))))
+
+    def shard_symbols(seed, n_total, lo, hi):
+        s = torch.empty((hi - lo) * REC_LEN, dtype=torch.uint8, device=dev)
+        for a in range(lo, hi, 2048):
+            b = min(hi, a + 2048)
+            s[(a - lo) * REC_LEN:(b - lo) * REC_LEN] = q.quantize(
+                synth.corpus_cuda_range(seed, n_total, a, b, L_SAMPLES, torch.float32, dev)).reshape(-1)
+        return s
+
+    def run(shard, m, tlog, reps, st=None):
+        """-> (best seconds (max over ranks), pairs, counts, per-step stream lengths summed over ranks)"""
+        best = None
+        for _ in range(reps):
+            if world == 1:
+                tr = st if st is not None else Trainer(shard.numel(), m, device=dev, table_log2=tlog)
+                tr.load(shard)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                pairs, counts, ntied = tr.run(m)
+                dt = time.perf_counter() - t0
+                lens = tr.lengths(len(pairs)).astype(np.float64)
+                st = tr
+            else:
+                if st is None:
+                    st = ShardedTrainer(shard.numel(), m, table_log2=tlog)
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                pairs, counts, ntied = st.train(shard, m)
+                d = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                dist.all_reduce(d, op=dist.ReduceOp.MAX)
+                dt = float(d)
+                l = torch.from_numpy(st.tr.lengths(len(pairs)).astype(np.float64)).to(dev)
+                dist.all_reduce(l)
+                lens = l.cpu().numpy()
+            best = dt if best is None else min(best, dt)
+        if world > 1:
+            dist.barrier()
+            st.close()
+        return best, pairs, counts, lens
+
+    progress("training: config 1")
+    # ---- config 1 ----
+    xc = synth.corpus(0, 1000, L_SAMPLES, np.float32)
+    sym = q.quantize(torch.from_numpy(xc).to(dev)).reshape(-1)
+    n1 = sym.numel()
+    lo, hi = split_contiguous(n1, world)[rank]
+    m1 = 5000
+    t1, pairs, counts, lens1 = run(sym[lo:hi].contiguous(), m1, 0, 3)
+    if not (np.array_equal(pairs, f["pairs"].astype(np.uint32)) and np.array_equal(counts, f["counts"])):
+        raise SystemExit("bench.py: PARITY FAILURE (merge list differs from the oracle fixture)")
+    alg1 = float(np.sum(2.0 * (lens1[:-1] + lens1[1:])))  # SURVEY.md 8d: 2*(n_t + n_{t+1}) bytes per step
+    out = {"metric": "BPE-train merges/sec", "value": m1 / t1, "unit": "merges/s", "seconds": t1,
+           "config": "config 1: 1,000 records = %d symbols, %d merges" % (n1, m1), "gpus": world,
+           "kernel": "train_loop_kernel (1 GPU, persistent)" if world == 1 else
+                     "dist_loop_kernel x%d (persistent, shard records + histogram patches written into the peers' memory over NVLink)" % world,
+           "final_tokens": int(lens1[-1]), "algorithmic_bytes": alg1, "achieved_gbs": alg1 / t1 / 1e9,
+           "frac_of_hbm_peak": alg1 / t1 / 1e9 / (peak * world), "gpu_launches": 2 if world == 1 else 6,
+           "parity": "merge list == oracle fixture (5000 merges)"}
+    if world > 1:
+        # the auto policy: a corpus whose token buffers fit one GPU with room to spare is trained on one GPU
+        # (the tail of a small corpus is latency, not bandwidth, and one GPU has the lowest latency)
+        t_single = None
+        if rank == 0:
+            tr = Trainer(n1, m1, device=dev)
+            for _ in range(2):
+                tr.load(sym)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                p1, c1, _ = tr.run(m1)
+                dt = time.perf_counter() - t0
+                t_single = dt if t_single is None else min(t_single, dt)
+            assert np.array_equal(p1, pairs)
+            del tr
         dist.barrier()
-        torch.cuda.synchronize(dev)
+        if rank == 0:
+            out["auto_policy"] = {"rule": "shard only when the corpus exceeds ecgbyte.dist_train.SHARD_MIN_SYMBOLS per run "
+                                          "(streaming-bound); below it rank 0 trains alone and broadcasts the merges",
+                                  "single_gpu_seconds": t_single, "single_gpu_merges_per_s": m1 / t_single,
+                                  "sharded_over_single": t_single / t1}
+    del sym
+
+    # ---- config 4 ----
+    if not args.no_config4:
+        progress("training: config-4 sub-corpus parity")
+        # (a) parity on a CPU-holdable sub-corpus through the same code path
+        n_sub, m_sub = 200, 300
+        lo, hi = split_contiguous(n_sub, world)[rank]
+        sub = shard_symbols(0, n_sub, lo, hi)
+        _, p_sub, c_sub, _ = run(sub, m_sub, 0, 1)
+        if rank == 0:
+            full = shard_symbols(0, n_sub, 0, n_sub).cpu().numpy()
+            _, o_pairs, o_counts, _ = O.train_pairs(full, m_sub, fast=True)
+            if not (np.array_equal(p_sub, o_pairs) and np.array_equal(c_sub, o_counts)):
+                raise SystemExit("bench.py: PARITY FAILURE (config-4 sub-corpus merge list differs from the oracle)")
+        del sub
+        progress("training: config 4, generating the corpus")
+        # (b) the full corpus
+        n4, m4 = args.config4_records, args.config4_merges
+        lo, hi = split_contiguous(n4, world)[rank]
         t0 = time.perf_counter()
-        pairs, counts, ntied, tr = train_shard(shard, m, device=dev)
+        shard = shard_symbols(0, n4, lo, hi)
         torch.cuda.synchronize(dev)
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        best = float(dt) if best is None else min(best, float(dt))
-    ok = bool(np.array_equal(pairs, f["pairs"].astype(np.uint32)) and np.array_equal(counts, f["counts"]))
-    if not ok:
-        raise SystemExit("bench.py: PARITY FAILURE (sharded merge list differs from the oracle fixture)")
-    return {"metric": "BPE-train merges/sec", "value": m / best, "unit": "merges/s", "seconds": best,
-            "corpus_symbols": int(sym.numel()), "merges": m, "shards": world,
-            "exchange": "2 NCCL all-gathers per merge step (boundary records, histogram delta lists)",
-            "parity": "merge list == oracle fixture (5000 merges)"}
+        gen = time.perf_counter() - t0
+        progress("training: config 4, %d symbols on this rank" % shard.numel())
+        t4, p4, c4, lens4 = run(shard, m4, 26, 1)
+        progress("training: config 4 done in %.1f s" % t4)
+        del shard
+        alg4 = float(np.sum(2.0 * (lens4[:-1] + lens4[1:])))
+        out["config4"] = {"config": "config 4: %d records = %d symbols, %d merges" % (n4, int(lens4[0]), m4), "gpus": world,
+                          "value": len(p4) / t4, "unit": "merges/s", "seconds": t4, "merges_done": int(len(p4)),
+                          "final_tokens": int(lens4[-1]), "algorithmic_bytes": alg4, "achieved_gbs": alg4 / t4 / 1e9,
+                          "frac_of_hbm_peak": alg4 / t4 / 1e9 / (peak * world), "generate_seconds": gen,
+                          "merge_list_crc": crc(p4), "first_merges": np.asarray(p4[:3]).tolist(), "last_merge": np.asarray(p4[-1]).tolist(),
+                          "top_count": int(c4[0]),
+                          "parity": "sub-corpus (%d records, %d merges) through the same path == oracle; compare merge_list_crc across N"
+                                    % (n_sub, m_sub)}
+    return out
 
 
 def main():
@@ -437,6 +733,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-i16", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--config4-records", type=int, default=250000)
+    ap.add_argument("--config4-merges", type=int, default=20000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

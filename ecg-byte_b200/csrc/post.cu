@@ -186,6 +186,48 @@ __global__ void __launch_bounds__(256) token_hist_kernel(const int32_t *__restri
             if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
     }
 }
+// ------------------------------------------------------------------ compact (CSR) token output
+// The encoder writes int32 rows of out_stride slots; what a host consumer needs is the tokens themselves:
+// 2-byte ids (< 65 536 by construction), rows back to back.  One CTA scans the lengths, all CTAs copy.
+__global__ void __launch_bounds__(1024) csr_offsets_kernel(const int32_t *__restrict__ len, size_t n_rec, size_t in_stride,
+                                                           unsigned long long *__restrict__ off) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t c0 = 0; c0 < n_rec; c0 += 1024) {
+        const size_t r = c0 + threadIdx.x;
+        unsigned long long x = 0;
+        if (r < n_rec) x = (unsigned long long)min((size_t)max(len[r], 0), in_stride);  // tokens beyond the stride were only counted
+        unsigned long long incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long before = s_base;
+        for (int q = 0; q < warp; q++) before += s_warp[q];
+        if (r < n_rec) off[r] = before + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n_rec] = s_base;
+}
+
+__global__ void __launch_bounds__(256) csr_copy_kernel(const int32_t *__restrict__ tok, size_t in_stride, const int32_t *__restrict__ len,
+                                                       size_t n_rec, const unsigned long long *__restrict__ off, uint16_t *__restrict__ out) {
+    for (size_t r = blockIdx.x; r < n_rec; r += gridDim.x) {
+        const size_t n = min((size_t)max(len[r], 0), in_stride);
+        const int32_t *src = tok + r * in_stride;
+        uint16_t *dst = out + off[r];
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint16_t)src[i];
+    }
+}
+
 }  // namespace ecgb
 
 using namespace ecgb;
@@ -298,6 +340,25 @@ extern "C" int ecgb_pack_training(const int32_t *d_tokens, size_t in_stride, con
         reinterpret_cast<const long long *>(d_text), reinterpret_cast<const unsigned long long *>(d_text_off), d_q_len, c,
         reinterpret_cast<long long *>(d_input_ids), d_attn_mask, reinterpret_cast<long long *>(d_labels),
         reinterpret_cast<long long *>(d_position_ids), d_status);
+    ECGB_CUDA(cudaGetLastError());
+    return ECGB_OK;
+}
+
+// Compact copy of the encoder's output: rows of 2-byte token ids back to back (CSR).  d_off[n_rec + 1] receives
+// the row offsets in tokens (d_off[n_rec] = total); d_out needs room for sum(min(len, in_stride)) tokens.
+extern "C" int ecgb_tokens_csr(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec, uint16_t *d_out,
+                               uint64_t *d_off, int device, void *stream) {
+    ECGB_REQUIRE(d_off, "d_off is NULL");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = as_stream(stream);
+    ECGB_REQUIRE(n_rec == 0 || (d_tokens && d_len && d_out), "NULL buffer");
+    csr_offsets_kernel<<<1, 1024, 0, st>>>(d_len, n_rec, in_stride, reinterpret_cast<unsigned long long *>(d_off));
+    if (n_rec) {
+        const unsigned grid = (unsigned)std::min<size_t>(n_rec, (size_t)sm_count(device) * 8);
+        csr_copy_kernel<<<grid, 256, 0, st>>>(d_tokens, in_stride, d_len, n_rec, reinterpret_cast<const unsigned long long *>(d_off), d_out);
+    }
     ECGB_CUDA(cudaGetLastError());
     return ECGB_OK;
 }

@@ -57,6 +57,7 @@ def _declare(L):
         "ecgb_decode_symbols": ([vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
         "ecgb_dequantize": ([dbl, dbl, vp, sz, vp, i32, vp], i32),
         "ecgb_expand_attention": ([vp, vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
+        "ecgb_tokens_csr": ([vp, sz, vp, sz, vp, vp, i32, vp], i32),
         "ecgb_token_histogram": ([vp, sz, vp, sz, u32, vp, i32, vp], i32),
         "ecgb_minmax": ([vp, i32, sz, C.POINTER(dbl), C.POINTER(dbl), i32, vp], i32),
         "ecgb_percentiles": ([vp, sz, vp, i32, vp, i32, vp], i32),
@@ -69,6 +70,7 @@ def _declare(L):
         "ecgb_trainer_length": ([vp, C.POINTER(u64)], i32),
         "ecgb_trainer_ids_host": ([vp, vp, u64, C.POINTER(u64)], i32),
         "ecgb_trainer_lengths": ([vp, u32, vp], i32),
+        "ecgb_trainer_table_stats": ([vp, vp], i32),
         "ecgb_trainer_histogram": ([vp, vp, vp, u64, C.POINTER(u64)], i32),
         "ecgb_trainer_dist_sizes": ([vp, C.POINTER(u32), C.POINTER(u32)], i32),
         "ecgb_trainer_dist_begin": ([vp, i32, i32, vp, vp], i32),

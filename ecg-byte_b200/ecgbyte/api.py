@@ -352,6 +352,64 @@ class EncodePipeline:
         return k  # kernel launches
 
 
+class EncodePipelineCSR(EncodePipeline):
+    """EncodePipeline with compact output: what crosses PCIe on the way back is 2 bytes per token plus 4 bytes per
+    record (lengths), instead of a padded int32 row of out_stride slots.  Record r's tokens are
+    tokens16[off[r]:off[r + 1]] with off = concatenate([0], cumsum(lens)) (records in input order).
+
+    The exact byte count of a chunk is only known on the device, so its token copy is issued one chunk late: while
+    chunk k's input is in flight the host reads chunk k-1's total (a 8-byte copy that finished long before) and
+    enqueues exactly that many bytes -- no padding is transferred and no stream is ever idle."""
+
+    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
+        super().__init__(vocab, quantizer, rec_len, out_stride, chunk, depth)
+        dev = self.dev
+        self.d_tok16 = [torch.empty((chunk * out_stride,), dtype=torch.uint16, device=dev) for _ in range(depth)]
+        self.d_off = [torch.empty((chunk + 1,), dtype=torch.int64, device=dev) for _ in range(depth)]
+        self.h_tot = [torch.zeros((1,), dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+
+    def run(self, x_pinned, tokens16_pinned, lens_pinned):
+        """tokens16_pinned: flat pinned uint16 buffer with room for every token; returns (launches, total tokens)."""
+        n = x_pinned.shape[0]
+        x2 = x_pinned.view(n, self.rec_len)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        chunks = [(c0, min(self.chunk, n - c0)) for c0 in range(0, n, self.chunk)]
+        base = 0
+
+        def finish(k):  # chunk k's tokens: exact size, behind its own kernels on its own stream
+            nonlocal base
+            b = k % self.depth
+            self.ev[b].synchronize()
+            tot = int(self.h_tot[b][0])
+            if base + tot > tokens16_pinned.numel():
+                raise ValueError("tokens16 buffer too small")
+            with torch.cuda.stream(self.streams[b]):
+                tokens16_pinned[base:base + tot].copy_(self.d_tok16[b][:tot], non_blocking=True)
+            base += tot
+
+        for k, (c0, m) in enumerate(chunks):
+            b = k % self.depth
+            with torch.cuda.stream(self.streams[b]):
+                self.d_in[b][:m].copy_(x2[c0:c0 + m], non_blocking=True)
+                self.vocab.encode_batch(self.q, self.d_in[b][:m], out_stride=self.out_stride,
+                                        tokens=self.d_tok[b], lens=self.d_len[b])
+                check(lib().ecgb_tokens_csr(_ptr(self.d_tok[b]), self.out_stride, _ptr(self.d_len[b]), m, _ptr(self.d_tok16[b]),
+                                            _ptr(self.d_off[b]), self.dev.index, _stream(self.dev)))
+                self.h_tot[b].copy_(self.d_off[b][m:m + 1], non_blocking=True)
+                lens_pinned[c0:c0 + m].copy_(self.d_len[b][:m], non_blocking=True)
+                self.ev[b].record()
+            if k >= 1:
+                finish(k - 1)
+        if chunks:
+            finish(len(chunks) - 1)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return 3 * len(chunks), base
+
+
 def expand_merges(pairs):
     """pairs [M, 2] -> (seq u32, off u64[M+1]): the expanded sequences (lib.rs:101-110)."""
     pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
@@ -421,6 +479,12 @@ class Trainer:
         out = np.zeros(int(n_steps) + 1, np.uint64)
         check(lib().ecgb_trainer_lengths(self._h, int(n_steps), _np(out)))
         return out
+
+    def table_stats(self):
+        """{'used', 'capacity', 'candidates', 'overflow'} of the pair table."""
+        out = np.zeros(4, np.uint64)
+        check(lib().ecgb_trainer_table_stats(self._h, _np(out)))
+        return {"used": int(out[0]), "capacity": int(out[1]), "candidates": int(out[2]), "overflow": int(out[3])}
 
     def histogram(self):
         """{(left, right): count} of the live pair histogram."""

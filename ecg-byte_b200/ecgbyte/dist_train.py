@@ -163,6 +163,58 @@ def train_shard_persistent(shard, num_merges, exchange=None, device=None, table_
     return pairs, counts, ntied, st.tr
 
 
+# Below this many symbols (whole corpus) a sharded run loses to one GPU: the tail of a small corpus is a chain of
+# latencies (argmax, barrier, exchange), not bandwidth.  Measured on B200s: 6e7 symbols -> 2 GPUs are 0.73x of one,
+# 1.2e9 symbols -> 1.65x; the switch-over is placed between the two.
+SHARD_MIN_SYMBOLS = 250_000_000
+
+
+def train_corpus_auto(shard, num_merges, exchange=None, device=None, table_log2=0):
+    """byte_pair_encoding over a corpus that already lies in contiguous shards on the ranks: sharded
+    (ShardedTrainer) when the corpus is large enough to be bandwidth-bound, otherwise gathered onto rank 0,
+    trained there by the single-device loop and the merge list broadcast.  -> (pairs, counts, ntied), identical
+    on every rank."""
+    import torch.distributed as dist
+    ex = exchange or TorchExchange()
+    dev = shard.device
+    n = torch.tensor([shard.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ex.world)]
+    dist.all_gather(sizes, n, group=ex.group)
+    sizes = [int(s) for s in sizes]
+    total = sum(sizes)
+    if ex.world == 1 or total >= SHARD_MIN_SYMBOLS:
+        st = ShardedTrainer(shard.numel(), num_merges, exchange=ex, device=device, table_log2=table_log2)
+        try:
+            res = st.train(shard, num_merges)
+            ex.barrier()
+        finally:
+            st.close()
+        return res
+    mx = max(sizes)
+    pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    pad[: shard.numel()] = shard
+    parts = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(ex.world)] if ex.rank == 0 else None
+    dist.gather(pad, parts, dst=0, group=ex.group)
+    m = int(num_merges)
+    res = torch.zeros((m, 4), dtype=torch.int64, device=dev)  # left, right, count, ntied
+    done = torch.zeros(1, dtype=torch.int64, device=dev)
+    if ex.rank == 0:
+        corpus = torch.cat([p[:s] for p, s in zip(parts, sizes)])
+        tr = Trainer(max(corpus.numel(), 1), m, device=device, table_log2=table_log2)
+        tr.load(corpus)
+        pairs, counts, ntied = tr.run(m)
+        d = len(pairs)
+        done[0] = d
+        res[:d, :2] = torch.from_numpy(pairs.astype(np.int64)).to(dev)
+        res[:d, 2] = torch.from_numpy(counts.astype(np.int64)).to(dev)
+        res[:d, 3] = torch.from_numpy(ntied.astype(np.int64)).to(dev)
+    dist.broadcast(done, 0, group=ex.group)
+    dist.broadcast(res, 0, group=ex.group)
+    d = int(done)
+    r = res[:d].cpu().numpy()
+    return r[:, :2].astype(np.uint32), r[:, 2].astype(np.uint64), r[:, 3].astype(np.uint32)
+
+
 def train_shards_persistent_local(shards, num_merges, device=None, table_log2=0, max_ctas=0, timeout_s=10.0):
     """The persistent sharded loop with every 'rank' in this process on ONE device, as ONE cooperative launch
     (blockIdx.y = rank, so all ranks are co-resident by construction), exchanging through plain device

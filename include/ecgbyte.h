@@ -159,6 +159,11 @@ int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens, size_t n_r
 int ecgb_expand_attention(const ecgb_vocab *v, const int32_t *d_tokens, const float *d_attn, size_t n_rec,
                           size_t in_stride, const int32_t *d_len, float *d_out, size_t out_stride,
                           int32_t *d_out_len, void *stream);
+/* Compact (CSR) copy of the encoder's output for host consumers of ecgb_encode_batch (the list[int] that
+ * rust_bpe.encode_text returns, lib.rs:192, per record): 2-byte ids (ids < 65 536), rows back to back.
+ * d_off[n_rec + 1] = row offsets in tokens, d_off[n_rec] = total; d_out holds sum(min(len, in_stride)). */
+int ecgb_tokens_csr(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec, uint16_t *d_out,
+                    uint64_t *d_off, int device, void *stream);
 /* analyze_token_distribution (tokenizer_utils.py:30-54): Counter over the encoded ids of a batch.
  * d_counts[n_ids] (u64, device) is ACCUMULATED into -- zero it first; the per-record token_lengths
  * of the reference are the encoder's d_len.  An id outside [0, n_ids) is ECGB_EINVAL. */
@@ -227,6 +232,8 @@ int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t cap, uint64
 
 /* h_n[i] = length of this shard's token stream after i merge steps, i in [0, n_steps] */
 int ecgb_trainer_lengths(ecgb_trainer *t, uint32_t n_steps, uint64_t *h_n);
+/* pair-table occupancy: h_out = {slots claimed, capacity, argmax candidates listed, overflow flag} */
+int ecgb_trainer_table_stats(ecgb_trainer *t, uint64_t h_out[4]);
 /* every pair with a non-zero count in the live histogram (== get_stats, lib.rs:28-48, of
  * the current stream); two-call sizing through *n_out / ECGB_ECAPACITY */
 int ecgb_trainer_histogram(ecgb_trainer *t, uint32_t *h_pairs, int64_t *h_counts, uint64_t cap,

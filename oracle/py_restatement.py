@@ -191,3 +191,15 @@ def token_distribution(encoded_records):
         counts.update(int(i) for i in ids)
         lengths.append(len(ids))
     return counts, lengths
+
+
+def normalize_all_as_written(signal, p1, p99):
+    """tu.py:14-19 the way the reference EXECUTES it: float arithmetic in NumPy, then one Python call per sample
+    through np.vectorize to map codes to letters, and (tu.py:59 / data_loader.py:75) ''.join over the flattened
+    '<U1' array.  Only used to time the reference's own NumPy path beside the C port (bench.py cpu_baseline)."""
+    s = np.asarray(signal)
+    normalized = (s - (p1 - 0.5)) / ((p99 + 0.5) - (p1 - 0.5) + 1e-6)
+    clipped = np.clip(normalized, 0, 1)
+    scaled = np.minimum(np.floor(clipped * len(ALPHABET)), len(ALPHABET) - 1).astype(np.uint8)
+    symbols = np.vectorize(lambda c: ALPHABET[c])(scaled)
+    return clipped, "".join(symbols.flatten())

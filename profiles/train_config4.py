@@ -37,6 +37,7 @@ if world == 1:
     pairs, counts, ntied = tr.run(m)
     dt = time.perf_counter() - t0
     lens = tr.lengths(len(pairs)).astype(np.float64)
+    print("pair table:", tr.table_stats(), file=sys.stderr, flush=True)
 else:
     st = ShardedTrainer(shard.numel(), m, table_log2=tlog)
     torch.cuda.synchronize(); dist.barrier()
@@ -48,6 +49,8 @@ else:
     l = torch.from_numpy(st.tr.lengths(len(pairs)).astype(np.float64)).to(dev)
     dist.all_reduce(l)
     lens = l.cpu().numpy()
+    if rank == 0:
+        print("pair table:", st.tr.table_stats(), file=sys.stderr, flush=True)
 alg = float(np.sum(2.0 * (lens[:-1] + lens[1:])))
 if rank == 0:
     peak = 6553.0

@@ -217,3 +217,37 @@ def test_token_histogram_matches_counter(tmp_path):
     assert h2[n_ids:].sum() == 0
     with pytest.raises(ValueError):
         token_histogram(tokens, lens, 100)   # ids >= 100 occur
+
+
+def test_encode_pipeline_csr(oracle, small_corpus, small_table):
+    """Host-buffer pipeline with compact output (2-byte ids, rows back to back, exact-size copies) == oracle,
+    over several chunks, and == the padded int32 pipeline."""
+    from ecgbyte.api import EncodePipeline, EncodePipelineCSR, Quantizer, Vocab
+    x, pct = small_corpus
+    _, vocab, merges = small_table
+    n = x.shape[0]
+    q = Quantizer(pct, dtype=torch.float32, device="cuda:0")
+    v = Vocab(merges, device="cuda:0")
+    rec_len = x.shape[1] * x.shape[2]
+    stride = 2048
+    xh = torch.from_numpy(x.astype(np.float32)).pin_memory()
+    tok16 = torch.zeros(n * stride, dtype=torch.uint16).pin_memory()
+    lens = torch.zeros(n, dtype=torch.int32).pin_memory()
+    pipe = EncodePipelineCSR(v, q, rec_len, stride, chunk=3, depth=2)   # ragged last chunk, slots reused
+    launches, total = pipe.run(xh, tok16, lens)
+    torch.cuda.synchronize()
+    assert total == int(lens.sum())
+    off = np.concatenate([[0], np.cumsum(lens.numpy().astype(np.int64))])
+    trie = oracle.Trie(merges=merges)
+    t16 = tok16.numpy()
+    for r in range(n):
+        sym = oracle.quantize(x[r].astype(np.float32), pct["percentile_1"], pct["percentile_99"]).reshape(-1)
+        want = trie.encode(sym)
+        np.testing.assert_array_equal(t16[off[r]:off[r + 1]].astype(np.uint32), want.astype(np.uint32))
+    tok32 = torch.zeros((n, stride), dtype=torch.int32).pin_memory()
+    lens2 = torch.zeros(n, dtype=torch.int32).pin_memory()
+    EncodePipeline(v, q, rec_len, stride, chunk=3, depth=2).run(xh, tok32, lens2)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lens.numpy(), lens2.numpy())
+    for r in range(n):
+        np.testing.assert_array_equal(t16[off[r]:off[r + 1]].astype(np.int32), tok32[r, : lens2[r]].numpy())
