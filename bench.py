@@ -659,26 +659,27 @@ def bench_train(args, dev, pct, peak, rank, world):
            "frac_of_hbm_peak": alg1 / t1 / 1e9 / (peak * world), "gpu_launches": 2 if world == 1 else 6,
            "parity": "merge list == oracle fixture (5000 merges)"}
     if world > 1:
-        # the auto policy: a corpus whose token buffers fit one GPU with room to spare is trained on one GPU
-        # (the tail of a small corpus is latency, not bandwidth, and one GPU has the lowest latency)
-        t_single = None
-        if rank == 0:
-            tr = Trainer(n1, m1, device=dev)
-            for _ in range(2):
-                tr.load(sym)
-                torch.cuda.synchronize(dev)
-                t0 = time.perf_counter()
-                p1, c1, _ = tr.run(m1)
-                dt = time.perf_counter() - t0
-                t_single = dt if t_single is None else min(t_single, dt)
-            assert np.array_equal(p1, pairs)
-            del tr
-        dist.barrier()
-        if rank == 0:
-            out["auto_policy"] = {"rule": "shard only when the corpus exceeds ecgbyte.dist_train.SHARD_MIN_SYMBOLS per run "
-                                          "(streaming-bound); below it rank 0 trains alone and broadcasts the merges",
-                                  "single_gpu_seconds": t_single, "single_gpu_merges_per_s": m1 / t_single,
-                                  "sharded_over_single": t_single / t1}
+        # the public entry point for a corpus that lies in shards on the ranks applies the auto policy: below
+        # SHARD_MIN_SYMBOLS the shards are gathered on rank 0, trained there by the single-device loop (the tail of a
+        # small corpus is a chain of latencies, and one GPU has the shortest chain) and the merges broadcast
+        from ecgbyte.dist_train import SHARD_MIN_SYMBOLS, train_corpus_auto
+        t_auto = None
+        for _ in range(3):
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            pa, ca, _ = train_corpus_auto(sym[lo:hi].contiguous(), m1)
+            d = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            t_auto = float(d) if t_auto is None else min(t_auto, float(d))
+        if not (np.array_equal(pa, pairs) and np.array_equal(ca, counts)):
+            raise SystemExit("bench.py: PARITY FAILURE (auto-policy merge list differs)")
+        out["sharded_forced"] = {k: out[k] for k in ("value", "unit", "seconds", "kernel", "achieved_gbs", "frac_of_hbm_peak", "gpu_launches")}
+        out.update({"value": m1 / t_auto, "seconds": t_auto, "achieved_gbs": alg1 / t_auto / 1e9,
+                    "frac_of_hbm_peak": alg1 / t_auto / 1e9 / peak, "gpu_launches": 2,
+                    "kernel": "ecgbyte.dist_train.train_corpus_auto: %d symbols < SHARD_MIN_SYMBOLS (%d) -> shards gathered over NCCL, "
+                              "train_loop_kernel on rank 0, merge list broadcast (gather and broadcast inside the timed region)"
+                              % (n1, SHARD_MIN_SYMBOLS)})
     del sym
 
     # ---- config 4 ----

@@ -22,31 +22,39 @@ _QUANT = {}
 
 
 def _quantizer(percentiles, dtype):
-    key = (float(percentiles["percentile_1"]), float(percentiles["percentile_99"]), dtype)
+    key = (float(percentiles["percentile_1"]), float(percentiles["percentile_99"]), dtype, torch.cuda.current_device())
     q = _QUANT.get(key)
     if q is None:
         q = _QUANT[key] = Quantizer(percentiles, dtype=dtype)
     return q
 
 
-def quantize_symbols(signal, percentiles):
-    """signal (any shape; float64 / float32 / int16) -> uint8 symbol codes 'a'..'z'."""
+def _as_samples(signal):
+    """The reference computes (signal - lo) / den on whatever np.load returned: float64 / float32 values as they
+    are, every integer type (int16 included) on its raw integer values.  Only the two float types have a kernel of
+    their own here; everything else is widened to float64 first, exactly like NumPy's promotion does.  (The 1e-3
+    de-scaling int16 path exists only behind the explicit Quantizer(dtype=int16, i16_scale=...) API.)"""
     x = np.ascontiguousarray(signal)
-    if x.dtype not in (np.float32, np.float64, np.int16):
+    if x.dtype not in (np.float32, np.float64):
         x = x.astype(np.float64)
+    return x
+
+
+def quantize_symbols(signal, percentiles):
+    """signal (any shape, any numeric dtype) -> uint8 symbol codes 'a'..'z'."""
+    x = _as_samples(signal)
     return _quantizer(percentiles, x.dtype).quantize_host(x)
 
 
 def normalize_all(signal, percentiles):
-    """-> (clipped_normalized float64 array, symbol_signal '<U1' array), tu.py:14-19."""
+    """-> (clipped_normalized array, symbol_signal '<U1' array), tu.py:14-19.  The symbols (the only output the
+    hot path uses: data_loader.py:74, tu.py:58) come from the device; the clipped values, which no caller on the
+    path reads, are the reference's own NumPy expression."""
     sig = np.asarray(signal)
     codes = quantize_symbols(sig, percentiles)
-    lo = percentiles["percentile_1"] - 0.5
-    den = (percentiles["percentile_99"] + 0.5) - (percentiles["percentile_1"] - 0.5) + 1e-6
-    x = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float64)).cuda()
-    # tensor / tensor is an IEEE divide (tensor / python-scalar multiplies by a reciprocal)
-    den_t = torch.tensor([float(den)], dtype=torch.float64, device=x.device)
-    clipped = torch.clamp((x - float(lo)) / den_t, 0, 1).cpu().numpy()
+    normalized = (sig - (percentiles["percentile_1"] - 0.5)) / (
+        (percentiles["percentile_99"] + 0.5) - (percentiles["percentile_1"] - 0.5) + 1e-6)
+    clipped = np.clip(normalized, 0, 1)
     symbol_signal = codes.view("S1").astype("<U1").reshape(sig.shape)
     return clipped, symbol_signal
 
@@ -65,16 +73,30 @@ def process_ecg(ecg, percentiles):
     return quantize_symbols(sig, percentiles).tobytes().decode("ascii")
 
 
-def process_large_file(file_path, percentiles, num_processes=None, n=None):
-    """tu.py:79-93: every listed record quantised and joined into ONE string, in file
-    order.  `num_processes` is accepted for compatibility (the GPU path needs no pool)."""
+def process_large_file(file_path, percentiles, num_processes=None, n=None, batch=256):
+    """tu.py:79-93: every listed record quantised and joined into ONE string, in file order; `n` caps the number
+    of lines read, each line is .strip()ped.  The reference fans the files out over `num_processes` worker
+    processes; here that many threads read the .npy files and runs of equally shaped records go to the device
+    as one batch (one copy in, one kernel, one copy out per up to `batch` files)."""
+    from concurrent.futures import ThreadPoolExecutor
     paths = []
     with open(file_path, "r") as f:
         for i, line in enumerate(f):
             if n is not None and i >= n:
                 break
             paths.append(line.strip())
-    parts = [process_ecg(p, percentiles) for p in paths]
+    parts = []
+    with ThreadPoolExecutor(max_workers=max(1, int(num_processes or 1))) as pool:
+        for s0 in range(0, len(paths), batch):
+            recs = [_as_samples(r) for r in pool.map(np.load, paths[s0:s0 + batch])]
+            k = 0
+            while k < len(recs):  # a run of records with one shape and dtype
+                e = k + 1
+                while e < len(recs) and recs[e].shape == recs[k].shape and recs[e].dtype == recs[k].dtype:
+                    e += 1
+                codes = _quantizer(percentiles, recs[k].dtype).quantize_host(np.stack(recs[k:e]))
+                parts.append(codes.tobytes().decode("ascii"))
+                k = e
     return "".join(parts)
 
 
@@ -101,7 +123,7 @@ def analyze_token_distribution(test_data, merges, percentiles, num_workers=None,
     """(token_counts: Counter, token_lengths: list[int]) over the records whose .npy paths are listed in
     test_data (tu.py:30-54).  Records are quantised + encoded in batches on the GPU and counted there;
     num_workers is accepted and ignored (the reference fans the files out over a process pool)."""
-    vocab = Vocab(merges)
+    vocab = rust_bpe._vocab_for(merges)
     n_ids = max([255] + [int(i) for _, i in merges]) + 1
     counts = torch.zeros((n_ids,), dtype=torch.int64, device="cuda")
     token_lengths = []
@@ -111,9 +133,7 @@ def analyze_token_distribution(test_data, merges, percentiles, num_workers=None,
         shapes = {r.shape for r in recs}
         groups = [recs] if len(shapes) == 1 else [[r] for r in recs]  # ragged shapes: one record per call
         for g in groups:
-            x = np.ascontiguousarray(np.stack(g))
-            if x.dtype not in (np.float32, np.float64, np.int16):
-                x = x.astype(np.float64)
+            x = _as_samples(np.stack(g))
             q = _quantizer(percentiles, x.dtype)
             tokens, lens = vocab.encode_batch(q, torch.from_numpy(x).cuda())
             token_histogram(tokens, lens, n_ids, counts)
@@ -123,20 +143,32 @@ def analyze_token_distribution(test_data, merges, percentiles, num_workers=None,
 
 
 def expand_attention(encoded_ids, attention_sequence, vocab, merges=None):
-    """runners/interpret.py:106-111: each token's attention value repeated once per symbol of the token.
-    With `merges` the expansion runs on the GPU (lengths from the vocabulary's decode table); without, the
-    lengths come from the vocab strings on the host exactly as the reference does."""
-    if merges is None:
+    """runners/interpret.py:106-111: each token's attention value repeated len(vocab[id]) times.  Without `merges`
+    that is done on the host exactly as the reference does.  With `merges` the device expands token INDICES (one per
+    base symbol, from the vocabulary's decode table) and the result is gathered from the caller's own values, so the
+    returned objects are the originals, not float32 roundings.  A vocab string is longer than its symbol count only
+    for raw bytes > 127 (spelled "<200>", lib.rs:50-56); such input takes the host path."""
+    ids = list(encoded_ids)
+    att = list(attention_sequence)
+    n = min(len(ids), len(att))
+
+    def host():
         out = []
-        for i, a in zip(encoded_ids, attention_sequence):
+        for i, a in zip(ids, att):
             out.extend([a] * len(vocab[i]))
         return out
-    n = min(len(encoded_ids), len(attention_sequence))
-    if n == 0:
-        return []
-    tok = torch.tensor(list(encoded_ids)[:n], dtype=torch.int32, device="cuda").view(1, n)
-    att = torch.tensor(list(attention_sequence)[:n], dtype=torch.float32, device="cuda").view(1, n)
+
+    if merges is None or n == 0 or any(127 < int(i) < 256 for i in ids[:n]):
+        return host()
+    v = rust_bpe._vocab_for(merges)
+    if getattr(v, "_has_high_bytes", None) is None:
+        v._has_high_bytes = bool((v.flat[0] > 127).any())
+    if v._has_high_bytes or n >= (1 << 24):
+        return host()
+    tok = torch.tensor(ids[:n], dtype=torch.int32, device="cuda").view(1, n)
+    idx = torch.arange(n, dtype=torch.float32, device="cuda").view(1, n)  # exact below 2^24
     lens = torch.tensor([n], dtype=torch.int32, device="cuda")
-    total = sum(len(vocab[int(i)]) for i in list(encoded_ids)[:n])
-    out, out_len = Vocab(merges).expand_attention(tok, lens, att, max(total, 1))
-    return out[0, : int(out_len[0])].cpu().tolist()
+    cap = n * int(v.info()["max_token_len"])
+    out, out_len = v.expand_attention(tok, lens, idx, max(cap, 1))
+    which = out[0, : int(out_len[0])].to(torch.int64).cpu().tolist()
+    return [att[j] for j in which]

@@ -54,22 +54,42 @@ def byte_pair_encoding(text, num_merges, num_threads=0):
     return ids, vocab, merges
 
 
+def _fingerprint(merges):
+    """Cheap content check of a merges list: its length and a spread of 16 entries (sequence length, id, first and
+    last symbol).  Enough to notice a list that was edited in place; an edit that keeps all sampled values is not
+    detected -- pass a new list object (the reference rebuilds its trie on every call, lib.rs:153-161)."""
+    n = len(merges)
+    fp = [n]
+    for k in range(16):
+        if n == 0:
+            break
+        seq, tid = merges[(k * n) // 16]
+        fp.append((len(seq), tid, seq[0] if len(seq) else -1, seq[-1] if len(seq) else -1))
+    return tuple(fp)
+
+
 def _vocab_for(merges):
-    """The reference rebuilds the trie on every call (lib.rs:153-161); here the
-    flattened trie is cached per merges object (identity + length)."""
+    """The reference rebuilds the trie on every call (lib.rs:153-161); here the flattened device trie is cached
+    per merges object: identity + a content fingerprint (see _fingerprint), and per device."""
+    import torch
     from ecgbyte.api import Vocab
 
-    key = (id(merges), len(merges))
+    for item in merges[:1]:
+        if not (isinstance(item, (tuple, list)) and len(item) == 2):
+            raise TypeError("argument 'merges': expected a list of (sequence, id) tuples")
+    key = (id(merges), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    fp = _fingerprint(merges)
     hit = _VOCAB_CACHE.get(key)
-    if hit is not None and hit[0] is merges:
+    if hit is not None and hit[0] is merges and hit[2] == fp:
         return hit[1]
     for item in merges:
         if not (isinstance(item, (tuple, list)) and len(item) == 2):
             raise TypeError("argument 'merges': expected a list of (sequence, id) tuples")
     v = Vocab(merges=merges)
+    _VOCAB_CACHE.pop(key, None)
     if len(_VOCAB_CACHE) >= _CACHE_MAX:
         _VOCAB_CACHE.pop(next(iter(_VOCAB_CACHE)))
-    _VOCAB_CACHE[key] = (merges, v)
+    _VOCAB_CACHE[key] = (merges, v, fp)
     return v
 
 
