@@ -40,6 +40,15 @@
 #ifndef ECGB_ENC_BURST
 #define ECGB_ENC_BURST 4
 #endif
+#ifndef ECGB_ENC_RING
+#define ECGB_ENC_RING 64      // ring capacity in symbols (a power of two)
+#endif
+#ifndef ECGB_ENC_HIST
+#define ECGB_ENC_HIST (1 << 20)  // symbols of history kept behind the cursor when the last terminal is further back
+#endif
+#ifndef ECGB_ENC_MAXB
+#define ECGB_ENC_MAXB 8
+#endif
 
 namespace ecgb {
 
@@ -58,9 +67,12 @@ struct Enc2Args {
 };
 
 constexpr int kG2 = 16;          // symbols per refill
-constexpr int kRing2 = 64;       // ring capacity in symbols (128 bytes per lane)
+constexpr int kRing2 = ECGB_ENC_RING;  // ring capacity in symbols (2 bytes each)
+constexpr int kHist = ECGB_ENC_HIST;
 constexpr int kBurst = ECGB_ENC_BURST;
-constexpr int kMaxBursts = 8;    // bursts per walk phase (at most one token per burst: the queue cannot overflow)
+constexpr int kMaxBursts = ECGB_ENC_MAXB;  // bursts per walk phase (at most one token per burst: the queue of 16 cannot overflow)
+static_assert(kMaxBursts <= 16 - 8, "token queue: 16 slots, flushed in eights");
+constexpr uint32_t kRingWordMask = (uint32_t)(kRing2 / 2 - 1) << 7;  // word index bits of a ring address
 constexpr int kThreads2 = 768;
 constexpr uint32_t kRingWarpBytes = 32u * kRing2 * 2u;
 constexpr uint32_t kQueueWarpBytes = 32u * 32u;
@@ -85,11 +97,11 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) { asm volatile(
 // ring entry of symbol position p, addressed by q2 = 2 * p: halfword (p & 63) of the lane's ring,
 // 32-bit words transposed inside the warp's 4 KB-aligned region (word w of lane l at (w * 32 + l) * 4)
 __device__ __forceinline__ uint32_t ring_at2(uint32_t ring_lane, int32_t q2) {
-    return ring_lane + (((uint32_t)q2 & 124u) << 5) + ((uint32_t)q2 & 2u);
+    return ring_lane + (((uint32_t)q2 & (uint32_t)(2 * kRing2 - 4)) << 5) + ((uint32_t)q2 & 2u);
 }
 // two entries further (one pair step): the word index lives in address bits 7..11
 __device__ __forceinline__ uint32_t ring_next(uint32_t ra) {
-    return ((ra + 128u) & 0xF80u) | (ra & ~0xF80u);  // one LOP3
+    return ((ra + 128u) & kRingWordMask) | (ra & ~kRingWordMask);  // one LOP3
 }
 // token queue slot of token number t (16 halfwords per lane, transposed the same way)
 __device__ __forceinline__ uint32_t queue_at(uint32_t queue_lane, uint32_t t) {
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
     // layout: [pad to 4 KB] rings | queues | ent | tok | aux
     const uint32_t nwarps = blockDim.x >> 5;
     const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t pad = (0u - smem_sa) & 4095u;
+    const uint32_t pad = (0u - smem_sa) & (kRingWarpBytes - 1u);
     uint8_t *s_rings = smem + pad;
     uint8_t *s_queues = s_rings + nwarps * kRingWarpBytes;
     const uint32_t n_ent = a.pv.n_ent;
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
         //     when the walker cannot run a burst otherwise -- over its own history (see `rewind`)
 #pragma unroll 1
         for (int g = 0; g < kRing2 / kG2; g++) {
-            const bool room = hi32 - (mq >> 1) <= kRing2 - kG2 - 2;
+            const bool room = hi32 - max(mq >> 1, (q >> 1) - kHist) <= kRing2 - kG2 - 2;
             const bool starved = hi32 - (q >> 1) < 2 * kBurst;
             const bool want = active && !closed && (room || starved);
             if (!__any_sync(FULL, want)) break;
@@ -429,7 +441,7 @@ static int launch_encode2_t(const Enc2Args &a, int exact_cells, int device, cuda
     int smem_max = 0;
     ECGB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     // tables + quantiser cells (or the byte -> class table) + slack to align the rings to 4 KB
-    const size_t aux = (DT == ECGB_U8 ? 256 : ((sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32 + 15) & ~(size_t)15)) + 4096;
+    const size_t aux = (DT == ECGB_U8 ? 256 : ((sizeof(QuantSmem<Thr>) + sizeof(Thr) * 32 + 15) & ~(size_t)15)) + kRingWarpBytes;
     const size_t ent_bytes = ((size_t)a.pv.n_ent * 4 + 15) & ~(size_t)15;
     const size_t tok_bytes = ((size_t)a.pv.n_ent * 2 + 15) & ~(size_t)15;
     const size_t per_warp = kRingWarpBytes + kQueueWarpBytes;

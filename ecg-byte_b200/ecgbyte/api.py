@@ -357,9 +357,9 @@ class EncodePipelineCSR(EncodePipeline):
     record (lengths), instead of a padded int32 row of out_stride slots.  Record r's tokens are
     tokens16[off[r]:off[r + 1]] with off = concatenate([0], cumsum(lens)) (records in input order).
 
-    The exact byte count of a chunk is only known on the device, so its token copy is issued one chunk late: while
-    chunk k's input is in flight the host reads chunk k-1's total (a 8-byte copy that finished long before) and
-    enqueues exactly that many bytes -- no padding is transferred and no stream is ever idle."""
+    The exact byte count of a chunk is only known on the device, so its token copy is issued late: while chunk k's
+    input is in flight the host reads the total of chunk k - (depth - 1) (an 8-byte copy that finished long before)
+    and enqueues exactly that many bytes -- no padding is transferred and the host never waits."""
 
     def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
         super().__init__(vocab, quantizer, rec_len, out_stride, chunk, depth)
@@ -378,6 +378,9 @@ class EncodePipelineCSR(EncodePipeline):
             s.wait_stream(cur)
         chunks = [(c0, min(self.chunk, n - c0)) for c0 in range(0, n, self.chunk)]
         base = 0
+        # a chunk's token copy is issued `lag` chunks late (its kernels finished long before, so reading its total never
+        # blocks the host); its slot is reused `depth` chunks later, on the same stream, i.e. behind that copy
+        lag = max(1, self.depth - 1)
 
         def finish(k):  # chunk k's tokens: exact size, behind its own kernels on its own stream
             nonlocal base
@@ -401,10 +404,10 @@ class EncodePipelineCSR(EncodePipeline):
                 self.h_tot[b].copy_(self.d_off[b][m:m + 1], non_blocking=True)
                 lens_pinned[c0:c0 + m].copy_(self.d_len[b][:m], non_blocking=True)
                 self.ev[b].record()
-            if k >= 1:
-                finish(k - 1)
-        if chunks:
-            finish(len(chunks) - 1)
+            if k >= lag:
+                finish(k - lag)
+        for k in range(max(len(chunks) - lag, 0), len(chunks)):
+            finish(k)
         for s in self.streams:
             cur.wait_stream(s)
         return 3 * len(chunks), base
