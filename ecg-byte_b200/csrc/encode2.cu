@@ -44,7 +44,8 @@
 #define ECGB_ENC_RING 64      // ring capacity in symbols (a power of two)
 #endif
 #ifndef ECGB_ENC_HIST
-#define ECGB_ENC_HIST (1 << 20)  // symbols of history kept behind the cursor when the last terminal is further back
+#define ECGB_ENC_HIST 16  // symbols of history kept behind the cursor when the last terminal is further back (a longer
+                          // look-back re-reads the record: rewind); unbounded history starves the lanes in long walks
 #endif
 #ifndef ECGB_ENC_MAXB
 #define ECGB_ENC_MAXB 8
@@ -478,9 +479,18 @@ int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact
                    int32_t *d_len, int device, cudaStream_t st) {
     if (!vv->pair.d_ent) return ECGB_EUNSUPPORTED;
     if (rec_len >= (1ull << 30)) return ECGB_EUNSUPPORTED;
-    // A/B knobs: ECGB_ENCODE_V1 forces the round-1 bitmap-trie kernel, ECGB_ENCODE_V2 this one
-    static const bool off = getenv("ECGB_ENCODE_V1") != nullptr || getenv("ECGB_ENCODE_V2") == nullptr;
-    if (off) return ECGB_EUNSUPPORTED;
+    // Which walker: measured on B200 (100 k records), the two-symbol-stride walker equals the bitmap-trie kernel while
+    // that kernel's whole trie sits in shared memory (5 000 merges: 13.96 vs 13.91 ms) and beats it once the trie
+    // spills to L2 (10 000 merges: 21.7 vs 27.4 ms) -- the pair table is 2.6x smaller.  So: this kernel when the
+    // 8-byte nodes do not fit next to 768 walkers' rings.  A/B knobs: ECGB_ENCODE_V1 / ECGB_ENCODE_V2 force one.
+    static const bool force_v1 = getenv("ECGB_ENCODE_V1") != nullptr, force_v2 = getenv("ECGB_ENCODE_V2") != nullptr;
+    if (force_v1) return ECGB_EUNSUPPORTED;
+    if (!force_v2) {
+        int smem_max = 0;
+        ECGB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const size_t trie_and_rings = (size_t)vv->n_nodes * 8 + 768 * 128 + 4096;
+        if (trie_and_rings <= (size_t)smem_max) return ECGB_EUNSUPPORTED;
+    }
     Enc2Args a{};
     a.in = d_in; a.n_total = n_total; a.n_rec = n_rec; a.rec_len = rec_len; a.offsets = d_offsets;
     a.tokens = d_tokens; a.out_stride = out_stride; a.lens = d_len;

@@ -231,3 +231,41 @@ def test_long_string_position_parallel(oracle, small_corpus, small_table):
         want = trie.encode(s)
         assert len(got) == len(want)
         np.testing.assert_array_equal(np.array(got, np.uint32), want)
+
+
+def test_encode_10k_merge_table_pair_walker(oracle):
+    """BASELINE config 3's table (10,000 merges, oracle fixture): its 8-byte trie nodes do not fit in shared memory next
+    to the walkers' rings, so the fused encoder dispatches to the two-symbol-stride pair-table walker (encode2.cu).
+    fp32, int16 and text input, ragged record count; == oracle."""
+    import os
+    from ecgbyte import synth
+    from ecgbyte.api import Quantizer, Vocab
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptbxl_1000_m10000.npz"))
+    pairs = f["pairs"].astype(np.uint32)
+    pct = {"percentile_1": np.float64(f["pct"][0]), "percentile_99": np.float64(f["pct"][1])}
+    v = Vocab.from_pairs(pairs, device="cuda:0")
+    info = v.info()
+    assert info["pair_slots"] > 0 and info["n_nodes"] * 8 + 768 * 128 > 227 * 1024
+    x = synth.corpus(99, 37, L=5000, dtype=np.float32)
+    sym = oracle.quantize(x, pct["percentile_1"], pct["percentile_99"]).reshape(37, -1)
+    seq, off = oracle.expand(pairs)
+    trie = oracle.Trie(flat=(seq, off, np.arange(256, 256 + len(pairs), dtype=np.uint32)))
+    w_tok, w_len = trie.encode_batch(sym, 8192)
+    q = Quantizer(pct, dtype=torch.float32, device="cuda:0")
+    tok, lens = v.encode_batch(q, torch.from_numpy(x).cuda(), out_stride=8192)
+    tok, lens = tok.cpu().numpy(), lens.cpu().numpy()
+    np.testing.assert_array_equal(lens, w_len.astype(np.int32))
+    for r in range(37):
+        np.testing.assert_array_equal(tok[r, : lens[r]], w_tok[r, : w_len[r]].astype(np.int32))
+    # the same symbols as text
+    tok2, lens2 = v.encode_symbols(torch.from_numpy(sym).cuda(), out_stride=8192)
+    np.testing.assert_array_equal(lens2.cpu().numpy(), lens)
+    np.testing.assert_array_equal(tok2.cpu().numpy()[3, : lens[3]], tok[3, : lens[3]])
+    # int16 records (explicit 1e-3 de-scaling API)
+    x16 = np.clip(np.round(x * 1000.0), -32768, 32767).astype(np.int16)
+    sym16 = oracle.quantize(x16, pct["percentile_1"], pct["percentile_99"]).reshape(37, -1)
+    w16, l16 = trie.encode_batch(sym16, 8192)
+    q16 = Quantizer(pct, dtype=torch.int16, device="cuda:0")
+    t16, n16 = v.encode_batch(q16, torch.from_numpy(x16).cuda(), out_stride=8192)
+    np.testing.assert_array_equal(n16.cpu().numpy(), l16.astype(np.int32))
+    np.testing.assert_array_equal(t16.cpu().numpy()[36, : l16[36]], w16[36, : l16[36]].astype(np.int32))
