@@ -456,7 +456,13 @@ static int launch_encode2_t(const Enc2Args &a, int exact_cells, int device, cuda
     // token ids in shared memory when that leaves at least 16 warps of walkers, else in L2
     const size_t fit_tok = (size_t)smem_max > ent_bytes + tok_bytes + aux ? ((size_t)smem_max - ent_bytes - tok_bytes - aux) / per_warp : 0;
     const size_t fit_notok = ((size_t)smem_max - ent_bytes - aux) / per_warp;
-    const bool toks = fit_tok >= std::min<size_t>(16, warps_max);
+    // ... unless leaving them in L2 saves a whole pass over the CTA's records (more walkers at once)
+    static const char *tok_knob = getenv("ECGB_ENC_TOKS");  // A/B: 0 = ids in L2, 1 = ids in shared memory when they fit
+    const size_t want_warps = std::min(warps_max, (per_cta + 31) / 32);
+    auto passes_with = [&](size_t fit) { const size_t c = std::min(warps_max, fit); return c ? (per_cta + c * 32 - 1) / (c * 32) : (size_t)1 << 30; };
+    bool toks = fit_tok >= std::min<size_t>(16, warps_max);
+    if (toks && fit_tok < want_warps && passes_with(fit_notok) < passes_with(fit_tok)) toks = false;
+    if (tok_knob) toks = atoi(tok_knob) != 0 && fit_tok >= 1;
     const size_t cap = std::min(warps_max, toks ? fit_tok : fit_notok);
     if (cap < 1) return ECGB_EUNSUPPORTED;
     // as few passes over the CTA's records as the walker limit allows, lanes spread evenly over them

@@ -127,6 +127,7 @@ struct TrainView {
     uint32_t resident_ok;     // resident tail enabled
     uint32_t redundant_max;   // train_loop_kernel: candidate lists up to this size are scanned by every CTA
     uint32_t cta_stride;      // CTA slots of partial / cta_bd / cta_counts (= SMs x kCtasPerSm)
+    const uint32_t *new_ids;  // id created by step i (NULL: 256 + i, lib.rs:97); set by ecgb_trainer_apply_pairs
     unsigned int *gbar;       // persistent sharded loop: arrival counter of its grid barrier (cumulative)
     unsigned int *abort;      // persistent sharded loop: set when a wait timed out; every spin loop gives up
     int rank, world;
@@ -624,7 +625,7 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
     // ranks of a sharded run (all_bd = every CTA's boundary record), so no output offsets are needed.
     static_assert(!(TICKETS && RESIDENT), "the resident tail belongs to the cooperative kernel");
     constexpr bool resident = RESIDENT;
-    const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = 256u + step;
+    const uint32_t a = bb.key >> 16, b = bb.key & 0xFFFFu, z = v.new_ids != nullptr ? v.new_ids[step] : 256u + step;
     const uint16_t *__restrict__ in = resident ? chunk : v.tok[step & 1];
     uint16_t *__restrict__ out = resident ? chunk : v.tok[(step + 1) & 1];
     const long long n = resident ? (long long)sm.chunk_n : (long long)v.dev->n[step & 1];
@@ -1954,6 +1955,49 @@ extern "C" int ecgb_trainer_lengths(ecgb_trainer *t, uint32_t n_steps, uint64_t 
     DeviceGuard g(t->device);
     ECGB_CUDA(cudaDeviceSynchronize());
     ECGB_CUDA(cudaMemcpy(h_n, t->v.n_hist, 8 * ((size_t)n_steps + 1), cudaMemcpyDeviceToHost));
+    return ECGB_OK;
+}
+
+// Apply a given list of merges, in order, to the loaded text: merge (lib.rs:10-26) once per pair, the id each
+// pair becomes given by the caller -- what the reference's track_encoding (tokenizer_utils.py:95-134) does with
+// pair-form merges.  No histogram, no argmax.  Read the result with ecgb_trainer_ids_host.
+extern "C" int ecgb_trainer_apply_pairs(ecgb_trainer *t, const uint32_t *h_pairs, const uint32_t *h_new_ids, uint32_t n) {
+    ECGB_REQUIRE(t, "trainer is NULL");
+    ECGB_REQUIRE(t->loaded && t->steps_done == 0 && !t->device_steps, "load the text first");
+    ECGB_REQUIRE(n <= t->max_merges, "%u merges > max_merges %u", n, t->max_merges);
+    ECGB_REQUIRE(n == 0 || (h_pairs && h_new_ids), "NULL argument");
+    for (uint32_t i = 0; i < n; i++)
+        ECGB_REQUIRE(h_pairs[2 * i] < kSentinel && h_pairs[2 * i + 1] < kSentinel && h_new_ids[i] < kSentinel,
+                     "merge %u: ids must be below 65535", i);
+    if (n == 0) return ECGB_OK;
+    DeviceGuard g(t->device);
+    cudaStream_t st = 0;
+    std::vector<Best> hb(n);
+    for (uint32_t i = 0; i < n; i++) hb[i] = Best{1ull, (h_pairs[2 * i] << 16) | h_pairs[2 * i + 1], 1u};
+    ECGB_CUDA(cudaMemcpy(t->v.best, hb.data(), sizeof(Best) * n, cudaMemcpyHostToDevice));
+    uint32_t *d_ids = nullptr;
+    int rc = dev_alloc(t, (void **)&d_ids, 4 * (size_t)n, false);
+    if (rc) return rc;
+    ECGB_CUDA(cudaMemcpy(d_ids, h_new_ids, 4 * (size_t)n, cudaMemcpyHostToDevice));
+    TrainView view = t->v;
+    view.new_ids = d_ids;
+    const int merge_grid = (int)std::min<uint64_t>((uint64_t)t->sms * 6, t->capacity / kTile + 1);
+    for (uint32_t step = 0; step < n; step++) {
+        merge_kernel<<<merge_grid, kTPB, 0, st>>>(view, step, nullptr, t->v.delta);
+        if ((step & 255u) == 255u) {  // the patches are not wanted: keep the delta table from filling up
+            const size_t dcap = (size_t)t->v.delta.mask + 1;
+            ECGB_CUDA(cudaMemsetAsync(t->v.delta.keys, 0xFF, dcap * 4, st));
+            ECGB_CUDA(cudaMemsetAsync(t->v.delta.cnt, 0, dcap * 8, st));
+            ECGB_CUDA(cudaMemsetAsync(t->v.delta.used, 0, 8, st));
+        }
+    }
+    ECGB_CUDA(cudaGetLastError());
+    ECGB_CUDA(cudaStreamSynchronize(st));
+    const size_t dcap = (size_t)t->v.delta.mask + 1;
+    ECGB_CUDA(cudaMemset(t->v.delta.keys, 0xFF, dcap * 4));
+    ECGB_CUDA(cudaMemset(t->v.delta.cnt, 0, dcap * 8));
+    ECGB_CUDA(cudaMemset(t->v.delta.used, 0, 8));
+    t->steps_done = n;
     return ECGB_OK;
 }
 

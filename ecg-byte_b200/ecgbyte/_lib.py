@@ -70,6 +70,7 @@ def _declare(L):
         "ecgb_trainer_length": ([vp, C.POINTER(u64)], i32),
         "ecgb_trainer_ids_host": ([vp, vp, u64, C.POINTER(u64)], i32),
         "ecgb_trainer_lengths": ([vp, u32, vp], i32),
+        "ecgb_trainer_apply_pairs": ([vp, vp, vp, u32], i32),
         "ecgb_trainer_table_stats": ([vp, vp], i32),
         "ecgb_trainer_histogram": ([vp, vp, vp, u64, C.POINTER(u64)], i32),
         "ecgb_trainer_dist_sizes": ([vp, C.POINTER(u32), C.POINTER(u32)], i32),

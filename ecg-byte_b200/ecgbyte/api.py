@@ -483,6 +483,13 @@ class Trainer:
         check(lib().ecgb_trainer_lengths(self._h, int(n_steps), _np(out)))
         return out
 
+    def apply_pairs(self, pairs, new_ids):
+        """Apply the merges (left, right) -> new id, in order, to the loaded text (no training)."""
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        new_ids = np.ascontiguousarray(new_ids, np.uint32).reshape(-1)
+        assert len(pairs) == len(new_ids)
+        check(lib().ecgb_trainer_apply_pairs(self._h, _np(pairs), _np(new_ids), len(new_ids)))
+
     def table_stats(self):
         """{'used', 'capacity', 'candidates', 'overflow'} of the pair table."""
         out = np.zeros(4, np.uint64)

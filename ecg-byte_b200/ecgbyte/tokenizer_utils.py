@@ -7,6 +7,7 @@ names, arguments and return values, computed by libecgbyte.so.
   save/load_vocab_and_merges                  tokenizer_utils.py:62-69
   analyze_token_distribution                  tokenizer_utils.py:30-54
   expand_attention                            runners/interpret.py:106-111
+  track_encoding                              tokenizer_utils.py:95-134
 """
 import pickle
 from collections import Counter
@@ -172,3 +173,33 @@ def expand_attention(encoded_ids, attention_sequence, vocab, merges=None):
     out, out_len = v.expand_attention(tok, lens, idx, max(cap, 1))
     which = out[0, : int(out_len[0])].to(torch.int64).cpu().tolist()
     return [att[j] for j in which]
+
+
+def track_encoding(text, merges, verbose=True):
+    """tokenizer_utils.py:95-134: apply `merges` to the UTF-8 bytes of `text` in order, each with merge()'s greedy
+    left-to-right rule (lib.rs:10-26), and return (ids, segment_map) where segment_map[k] = (start, end) byte range of
+    token k.  The reference tests `(ids[i], ids[i + 1]) == pair`, which can only hold when `pair` is a 2-tuple: with the
+    pickle's own format (`pair` = the expanded sequence, a list) nothing is ever merged -- same here.  Pair-form merges
+    run through the trainer's merge kernel on the device; `verbose` only switched a progress bar."""
+    from .api import Trainer
+    data = text.encode("utf-8")
+    todo = [(p, nid) for p, nid in merges
+            if isinstance(p, tuple) and len(p) == 2 and all(isinstance(x, int) and not isinstance(x, bool) for x in p)]
+    n = len(data)
+    if not todo or n == 0:
+        return list(data), [(i, i + 1) for i in range(n)]
+    length = {}
+    for (l, r), nid in todo:
+        if not (isinstance(nid, int) and 256 <= nid < 65535) or nid in length or not (0 <= l < 65535 and 0 <= r < 65535):
+            raise ValueError("track_encoding: merged ids must be distinct ints in [256, 65535)")
+        length[nid] = length.get(l, 1) + length.get(r, 1)
+    tr = Trainer(n, len(todo))
+    tr.load(data)
+    tr.apply_pairs([p for p, _ in todo], [nid for _, nid in todo])
+    ids = tr.ids()
+    lens = np.ones(65536, np.int64)
+    for nid, ln in length.items():
+        lens[nid] = ln
+    ends = np.cumsum(lens[ids])
+    starts = ends - lens[ids]
+    return ids.tolist(), list(zip(starts.tolist(), ends.tolist()))

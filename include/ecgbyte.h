@@ -232,6 +232,9 @@ int ecgb_trainer_ids_host(ecgb_trainer *t, uint32_t *h_ids, uint64_t cap, uint64
 
 /* h_n[i] = length of this shard's token stream after i merge steps, i in [0, n_steps] */
 int ecgb_trainer_lengths(ecgb_trainer *t, uint32_t n_steps, uint64_t *h_n);
+/* track_encoding (tokenizer_utils.py:95-134) with pair-form merges: apply the given (left, right) -> new id merges
+ * in order to the loaded text (merge, lib.rs:10-26, once per pair); result through ecgb_trainer_ids_host. */
+int ecgb_trainer_apply_pairs(ecgb_trainer *t, const uint32_t *h_pairs, const uint32_t *h_new_ids, uint32_t n);
 /* pair-table occupancy: h_out = {slots claimed, capacity, argmax candidates listed, overflow flag} */
 int ecgb_trainer_table_stats(ecgb_trainer *t, uint64_t h_out[4]);
 /* every pair with a non-zero count in the live histogram (== get_stats, lib.rs:28-48, of

@@ -4,6 +4,7 @@ Python call sites of the hot path (build container only; needs /root/reference):
   * ecg_byte.utils.tokenizer_utils.analyze_token_distribution            (tu.py:30-54)
   * ecg_byte.runners.interpret.expand_attention                          (runners/interpret.py:106-111)
   * ecg_byte.utils.tokenizer_utils.save_vocab_and_merges                 (tu.py:62-64)
+  * ecg_byte.utils.tokenizer_utils.track_encoding                        (tu.py:95-134)
 The native module rust_bpe cannot be built here (no Rust toolchain); where a reference function calls
 rust_bpe.encode_text the stub installed in sys.modules forwards to the C restatement of lib.rs:149-193
 (oracle/ecgb_oracle.c) -- everything around that call is the reference's unmodified code.
@@ -92,6 +93,23 @@ def main():
     store["ea_att_1"] = np.array(att1, np.float64)
     store["ea_out_1"] = np.array(ea(enc1, att1, vocab), np.float64)                                       # the reference
     store["ea_out_short"] = np.array(ea(enc[:7], att[:4], vocab), np.float64)                              # zip stops at the shorter
+
+    # ---- track_encoding: (a) the pickle's own format -- the expanded sequence is a list, so `(a, b) == pair` never holds
+    #      and nothing is merged; (b) pair-form merges, which it does apply, incl. an (x,x) pair on a run
+    txt = corpus[:1500]
+    ids_a, seg_a = tu.track_encoding(txt, merges, verbose=False)                                           # the reference
+    store["te_text"] = np.frombuffer(txt.encode(), np.uint8)
+    store["te_ids_listform"] = np.array(ids_a, np.int64)
+    store["te_seg_listform"] = np.array(seg_a, np.int64)
+    pair_form = [((int(l), int(r)), 256 + i) for i, (l, r) in enumerate(pairs.tolist())]
+    ids_b, seg_b = tu.track_encoding(txt, pair_form, verbose=False)                                        # the reference
+    store["te_ids_pairform"] = np.array(ids_b, np.int64)
+    store["te_seg_pairform"] = np.array(seg_b, np.int64)
+    runs = "aaaaaaabaaaabbbbbbbbbaaa"
+    pf2 = [((97, 97), 300), ((98, 98), 301), ((300, 300), 302), ((301, 97), 303)]
+    ids_c, seg_c = tu.track_encoding(runs, pf2)                                                            # the reference
+    store["te_runs_ids"] = np.array(ids_c, np.int64)
+    store["te_runs_seg"] = np.array(seg_c, np.int64)
 
     out = os.path.join(ROOT, "tests", "golden")
     np.savez_compressed(os.path.join(out, "callsites_reference.npz"), **store)

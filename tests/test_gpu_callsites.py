@@ -119,3 +119,23 @@ def test_train_tokenizer_call_sequence(tmp_path, oracle, gold, files):
     den = (percentiles["percentile_99"] + 0.5) - (percentiles["percentile_1"] - 0.5)
     inside = (new_ecg_signal > percentiles["percentile_1"] - 0.5) & (new_ecg_signal < percentiles["percentile_99"] + 0.5)
     assert np.max(np.abs(new_ecg_signal - decoded_signal)[inside]) <= den / 25.0     # :63 within one quantisation step
+
+
+def test_track_encoding_matches_reference(gold):
+    """tokenizer_utils.py:95-134 run by the reference itself: with the pickle's list-form merges nothing is merged;
+    pair-form merges are applied in order with merge()'s greedy rule (here: the trainer's merge kernel), incl. (x,x)
+    pairs on runs; segment_map is the byte range of every token."""
+    from ecgbyte import tokenizer_utils as tu
+    with open(PKL, "rb") as f:
+        vocab, merges = pickle.load(f)
+    txt = gold["te_text"].tobytes().decode()
+    ids, seg = tu.track_encoding(txt, merges)
+    assert ids == gold["te_ids_listform"].tolist() and [list(s) for s in seg] == gold["te_seg_listform"].tolist()
+    pair_form = [((int(l), int(r)), 256 + i) for i, (l, r) in enumerate(gold["pairs"].tolist())]
+    ids, seg = tu.track_encoding(txt, pair_form, verbose=False)
+    assert ids == gold["te_ids_pairform"].tolist()
+    assert [list(s) for s in seg] == gold["te_seg_pairform"].tolist()
+    assert all(isinstance(s, tuple) for s in seg)
+    ids, seg = tu.track_encoding("aaaaaaabaaaabbbbbbbbbaaa", [((97, 97), 300), ((98, 98), 301), ((300, 300), 302), ((301, 97), 303)])
+    assert ids == gold["te_runs_ids"].tolist() and [list(s) for s in seg] == gold["te_runs_seg"].tolist()
+    assert tu.track_encoding("", pair_form) == ([], [])
