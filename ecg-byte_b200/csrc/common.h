@@ -14,6 +14,25 @@ namespace ecgb {
 char *err_buf();
 int fail(int status, const char *fmt, ...);
 
+// Stream-ordered scratch allocation that is returned to the pool on EVERY exit path of the function that owns it
+// (the ECGB_CUDA / ECGB_REQUIRE macros return early on failure).
+template <class T>
+struct AsyncBuf {
+    T *p = nullptr;
+    cudaStream_t st = nullptr;
+    AsyncBuf() = default;
+    AsyncBuf(const AsyncBuf &) = delete;
+    AsyncBuf &operator=(const AsyncBuf &) = delete;
+    cudaError_t alloc(size_t count, cudaStream_t stream) {
+        st = stream;
+        return cudaMallocAsync(reinterpret_cast<void **>(&p), (count ? count : 1) * sizeof(T), stream);
+    }
+    ~AsyncBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    operator T *() const { return p; }
+};
+
 #define ECGB_CUDA(call)                                                                      \
     do {                                                                                     \
         cudaError_t e_ = (call);                                                             \

@@ -476,11 +476,10 @@ extern "C" int ecgb_encode_batch(const ecgb_vocab *v, const ecgb_quantizer *q, c
     cudaStream_t st = as_stream(stream);
     if (!vv->compact) {
         // wide vocabularies: quantise to a temporary symbol buffer, then the wide walker
-        uint8_t *d_sym = nullptr;
-        ECGB_CUDA(cudaMallocAsync((void **)&d_sym, n_rec * rec_len, st));
+        AsyncBuf<uint8_t> d_sym;  // released on every exit path
+        ECGB_CUDA(d_sym.alloc(n_rec * rec_len, st));
         int rc = ecgb_quantize(q, d_in, n_rec * rec_len, d_sym, stream);
         if (rc == ECGB_OK) rc = ecgb_encode_symbols(v, d_sym, n_rec, rec_len, nullptr, d_tokens, out_stride, d_len, stream);
-        cudaFreeAsync(d_sym, st);
         return rc;
     }
     {

@@ -127,14 +127,15 @@ int ecgb_encode_long_device(const ecgb_vocab *v, const uint8_t *d_text, size_t n
     const int device = ecgb_vocab_device(v);
     const int sms = sm_count(device);
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
-    uint16_t *d_len = nullptr, *d_tok = nullptr;
-    uint32_t *d_exit = nullptr, *d_entry = nullptr;
-    unsigned long long *d_counts = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_len, n * 2, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_tok, n * 2, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_exit, n * 4, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_entry, n_chunks * 4, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_counts, (n_chunks + 1) * 8, st));
+    // scratch from the stream's pool; released on every exit path
+    AsyncBuf<uint16_t> d_len, d_tok;
+    AsyncBuf<uint32_t> d_exit, d_entry;
+    AsyncBuf<unsigned long long> d_counts;
+    ECGB_CUDA(d_len.alloc(n, st));
+    ECGB_CUDA(d_tok.alloc(n, st));
+    ECGB_CUDA(d_exit.alloc(n, st));
+    ECGB_CUDA(d_entry.alloc(n_chunks, st));
+    ECGB_CUDA(d_counts.alloc(n_chunks + 1, st));
     const int gridA = (int)std::min<size_t>((size_t)sms * 8, (n + 255) / 256);
     long_match_kernel<<<gridA, 256, 0, st>>>(d_text, n, vv->d_nodes, vv->d_cls, d_len, d_tok);
     const int gridC = (int)((n_chunks + 127) / 128);
@@ -144,12 +145,7 @@ int ecgb_encode_long_device(const ecgb_vocab *v, const uint8_t *d_text, size_t n
     long_scan_kernel<<<1, 1024, 0, st>>>(d_counts, n_chunks);
     long_emit_kernel<<<gridC, 128, 0, st>>>(d_len, d_tok, n, d_entry, n_chunks, d_counts, d_out, cap, 1);
     ECGB_CUDA(cudaGetLastError());
-    ECGB_CUDA(cudaMemcpyAsync(h_count, d_counts + n_chunks, 8, cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(h_count, d_counts.p + n_chunks, 8, cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_len, st);
-    cudaFreeAsync(d_tok, st);
-    cudaFreeAsync(d_exit, st);
-    cudaFreeAsync(d_entry, st);
-    cudaFreeAsync(d_counts, st);
     return ECGB_OK;
 }

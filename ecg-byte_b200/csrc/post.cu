@@ -243,16 +243,15 @@ extern "C" int ecgb_decode_symbols(const ecgb_vocab *v, const int32_t *d_tokens,
     int device = ecgb_vocab_device(v);
     DeviceGuard g(device);
     cudaStream_t st = as_stream(stream);
-    int *d_bad = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
-    ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    AsyncBuf<int> d_bad;  // released on every exit path
+    ECGB_CUDA(d_bad.alloc(1, st));
+    ECGB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
     decode_kernel<false, uint8_t><<<(unsigned)n_rec, 256, 0, st>>>(d_tokens, in_stride, d_len, d_sym, sym_stride, d_sym_len,
                                                                    vv->d_dec_sym, vv->d_dec_off, vv->dec_ids, d_bad, nullptr);
     ECGB_CUDA(cudaGetLastError());
     int bad = 0;
-    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    ECGB_CUDA(cudaFreeAsync(d_bad, st));
     if (bad) return fail(ECGB_EINVAL, "a token id is not in the vocabulary (decode_text would raise KeyError)");
     return ECGB_OK;
 }
@@ -267,16 +266,15 @@ extern "C" int ecgb_expand_attention(const ecgb_vocab *v, const int32_t *d_token
     ECGB_REQUIRE(vv->d_dec_off != nullptr, "vocabulary has no decode table (token ids too large)");
     DeviceGuard g(ecgb_vocab_device(v));
     cudaStream_t st = as_stream(stream);
-    int *d_bad = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
-    ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    AsyncBuf<int> d_bad;  // released on every exit path
+    ECGB_CUDA(d_bad.alloc(1, st));
+    ECGB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
     decode_kernel<true, float><<<(unsigned)n_rec, 256, 0, st>>>(d_tokens, in_stride, d_len, d_out, out_stride, d_out_len,
                                                                 vv->d_dec_sym, vv->d_dec_off, vv->dec_ids, d_bad, d_attn);
     ECGB_CUDA(cudaGetLastError());
     int bad = 0;
-    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    ECGB_CUDA(cudaFreeAsync(d_bad, st));
     if (bad) return fail(ECGB_EINVAL, "a token id is not in the vocabulary (expand_attention would raise KeyError)");
     return ECGB_OK;
 }
@@ -288,9 +286,9 @@ extern "C" int ecgb_token_histogram(const int32_t *d_tokens, size_t in_stride, c
     ECGB_REQUIRE(n_ids > 0, "n_ids is 0");
     DeviceGuard g(device);
     cudaStream_t st = as_stream(stream);
-    int *d_bad = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_bad, sizeof(int), st));
-    ECGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    AsyncBuf<int> d_bad;  // released on every exit path
+    ECGB_CUDA(d_bad.alloc(1, st));
+    ECGB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
     int sms = 0;
     ECGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const bool priv = n_ids <= kHistSmemIds;
@@ -299,9 +297,8 @@ extern "C" int ecgb_token_histogram(const int32_t *d_tokens, size_t in_stride, c
     else token_hist_kernel<false><<<grid, 256, 0, st>>>(d_tokens, in_stride, d_len, n_rec, n_ids, d_counts, d_bad);
     ECGB_CUDA(cudaGetLastError());
     int bad = 0;
-    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    ECGB_CUDA(cudaFreeAsync(d_bad, st));
     if (bad) return fail(ECGB_EINVAL, "a token id is outside [0, n_ids)");
     return ECGB_OK;
 }

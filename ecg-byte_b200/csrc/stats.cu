@@ -108,22 +108,21 @@ extern "C" int ecgb_minmax(const void *d_in, ecgb_dtype dtype, size_t n, double 
     if (rc) return rc;
     DeviceGuard g(device);
     cudaStream_t st = as_stream(stream);
-    unsigned long long *d_out = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_out, 24, st));
+    AsyncBuf<unsigned long long> d_out;  // released on every exit path
+    ECGB_CUDA(d_out.alloc(3, st));
     const unsigned long long init[3] = {~0ull, 0ull, 0ull};
-    ECGB_CUDA(cudaMemcpyAsync(d_out, init, 24, cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaMemcpyAsync(d_out.p, init, 24, cudaMemcpyHostToDevice, st));
     const int grid = (int)std::min<size_t>((size_t)sm_count(device) * 8, (n / 4 + 255) / 256 + 1);
     switch (dtype) {
         case ECGB_F32: minmax_kernel<float><<<grid, 256, 0, st>>>((const float *)d_in, n, d_out); break;
         case ECGB_F64: minmax_kernel<double><<<grid, 256, 0, st>>>((const double *)d_in, n, d_out); break;
         case ECGB_I16: minmax_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)d_in, n, d_out); break;
-        default: cudaFreeAsync(d_out, st); return fail(ECGB_EINVAL, "unsupported dtype %d", (int)dtype);
+        default: return fail(ECGB_EINVAL, "unsupported dtype %d", (int)dtype);
     }
     ECGB_CUDA(cudaGetLastError());
     unsigned long long h[3];
-    ECGB_CUDA(cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(h, d_out.p, 24, cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    ECGB_CUDA(cudaFreeAsync(d_out, st));
     auto from_key = [](unsigned long long k) {
         unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
         double f;
@@ -164,26 +163,22 @@ extern "C" int ecgb_percentiles(const double *d_samples, size_t n, const double 
         ranks[2 * i + 1] = (unsigned long long)nxt;
         gamma[i] = virt - std::floor(virt);
     }
-    unsigned long long *d_ranks = nullptr;
-    double *d_vals = nullptr;
-    unsigned long long *d_mm = nullptr;
-    ECGB_CUDA(cudaMallocAsync((void **)&d_ranks, ranks.size() * 8, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_vals, ranks.size() * 8, st));
-    ECGB_CUDA(cudaMallocAsync((void **)&d_mm, 24, st));
+    AsyncBuf<unsigned long long> d_ranks, d_mm;  // released on every exit path
+    AsyncBuf<double> d_vals;
+    ECGB_CUDA(d_ranks.alloc(ranks.size(), st));
+    ECGB_CUDA(d_vals.alloc(ranks.size(), st));
+    ECGB_CUDA(d_mm.alloc(3, st));
     const unsigned long long init[3] = {~0ull, 0ull, 0ull};
-    ECGB_CUDA(cudaMemcpyAsync(d_mm, init, 24, cudaMemcpyHostToDevice, st));
-    ECGB_CUDA(cudaMemcpyAsync(d_ranks, ranks.data(), ranks.size() * 8, cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaMemcpyAsync(d_mm.p, init, 24, cudaMemcpyHostToDevice, st));
+    ECGB_CUDA(cudaMemcpyAsync(d_ranks.p, ranks.data(), ranks.size() * 8, cudaMemcpyHostToDevice, st));
     minmax_kernel<double><<<sm_count(device) * 2, 256, 0, st>>>(d_samples, n, d_mm);  // NaN detection
     select_kernel<<<2 * nq, 1024, 0, st>>>(d_samples, n, d_ranks, d_vals);
     ECGB_CUDA(cudaGetLastError());
     std::vector<double> vals(ranks.size());
     unsigned long long mm[3];
-    ECGB_CUDA(cudaMemcpyAsync(vals.data(), d_vals, vals.size() * 8, cudaMemcpyDeviceToHost, st));
-    ECGB_CUDA(cudaMemcpyAsync(mm, d_mm, 24, cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(vals.data(), d_vals.p, vals.size() * 8, cudaMemcpyDeviceToHost, st));
+    ECGB_CUDA(cudaMemcpyAsync(mm, d_mm.p, 24, cudaMemcpyDeviceToHost, st));
     ECGB_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_ranks, st);
-    cudaFreeAsync(d_vals, st);
-    cudaFreeAsync(d_mm, st);
     for (int i = 0; i < nq; i++) {
         if (mm[2]) { h_out[i] = std::numeric_limits<double>::quiet_NaN(); continue; }  // NaN in, NaN out
         // NumPy _lerp: a + (b - a) * t, and b - (b - a) * (1 - t) where t >= 0.5
