@@ -313,30 +313,30 @@ def run_ours(args, rank, world, local_rank):
     n_e2e = min(args.e2e_records, n_rec)
     xh = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.float32).pin_memory()
     xh.copy_(x[:n_e2e])
-    tok16_h = torch.empty((n_e2e * 6144,), dtype=torch.uint16).pin_memory()
+    tok16_h = torch.empty((n_e2e * stride,), dtype=torch.uint16).pin_memory()
     len_h = torch.empty((n_e2e,), dtype=torch.int32).pin_memory()
+    off_h = torch.empty((n_e2e,), dtype=torch.int64).pin_memory()
     pipe = EncodePipelineCSR(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
     e2e_steps = max(3, min(args.steps, 5))
 
-    def time_pipe(p, xin, tok_out):
+    def time_pipe(p, xin, *outs):
         for _ in range(2):
-            p.run(xin, tok_out, len_h)
+            p.run(xin, *outs)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        n_l, n_t = 0, 0
+        n_l = 0
         for _ in range(e2e_steps):
-            r = p.run(xin, tok_out, len_h)
-            n_l += r[0] if isinstance(r, tuple) else r
-            n_t = r[1] if isinstance(r, tuple) else 0
+            n_l += p.run(xin, *outs)   # consecutive steps pipeline into each other; every step copies in and out
         e1.record()
         barrier()
-        return e0.elapsed_time(e1), n_l, n_t
+        return e0.elapsed_time(e1), n_l
 
-    e2e_ms, launches_e2e, e2e_tokens = time_pipe(pipe, xh, tok16_h)
+    e2e_ms, launches_e2e = time_pipe(pipe, xh, tok16_h, len_h, off_h)
     assert np.array_equal(len_h.numpy(), lens_h[:n_e2e].astype(np.int32)), "e2e lengths differ from device-resident run"
-    e2e_tok_copy = tok16_h[:e2e_tokens].numpy().copy()
-    e2e_off = np.concatenate([[0], np.cumsum(lens_h[:n_e2e])])
+    e2e_tokens = int(len_h.numpy().astype(np.int64).sum())
+    e2e_off = off_h.numpy().copy()
+    e2e_tok_copy = [tok16_h[int(e2e_off[k]):int(e2e_off[k]) + int(lens_h[k])].numpy().copy() for k in range(min(8, n_e2e))]
 
     # the same pipeline fed with int16 records (1 uV/LSB, PTB-XL's native storage type): half the PCIe bytes per record
     e2e_i16_ms = None
@@ -346,13 +346,13 @@ def run_ours(args, rank, world, local_rank):
         xh16 = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.int16).pin_memory()
         xh16.copy_(x16)
         pipe16 = EncodePipelineCSR(v, q16, REC_LEN, stride, chunk=args.e2e_chunk)
-        e2e_i16_ms, _, i16_tokens = time_pipe(pipe16, xh16, tok16_h)
+        e2e_i16_ms, _ = time_pipe(pipe16, xh16, tok16_h, len_h, off_h)
         del x16, pipe16
 
     # padded int32 rows (round-1 output format), for comparison
     tok32_h = torch.empty((n_e2e, stride), dtype=torch.int32).pin_memory()
     pipe32 = EncodePipeline(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
-    e2e32_ms, _, _ = time_pipe(pipe32, xh, tok32_h)
+    e2e32_ms, _ = time_pipe(pipe32, xh, tok32_h, len_h)
     del pipe32
 
     progress("bare copy ceiling")
@@ -430,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
         if not np.array_equal(g_tok[k, : w_len[k]], w_tok[k, : w_len[k]].astype(np.int32)):
             bad.append("tokens of record %d" % idx[k])
     for k in range(min(8, n_e2e)):  # the host-buffer path (compact 2-byte output) returns the same tokens
-        if not np.array_equal(e2e_tok_copy[e2e_off[k]:e2e_off[k + 1]].astype(np.int32), g_tok[k, : lens_h[k]]):
+        if not np.array_equal(e2e_tok_copy[k].astype(np.int32), g_tok[k, : lens_h[k]]):
             bad.append("e2e tokens of record %d" % k)
     if bad:
         raise SystemExit("bench.py: PARITY FAILURE against the oracle (%s) -- numbers withheld" % ", ".join(bad[:5]))
@@ -488,9 +488,9 @@ def run_ours(args, rank, world, local_rank):
                                 "u8 symbols, 8-byte trie nodes, int32 tokens",
                   "tokens_per_record": total_tokens_all / (world * n_rec), "out_stride": stride, "host_numa": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n_e2e * rec_in_bytes),
-                "d2h_bytes_per_step": int(2 * e2e_tokens_all + 4 * world * n_e2e), "records_per_step": world * n_e2e, "steps": e2e_steps,
-                "api": "ecgbyte.api.EncodePipelineCSR.run (pinned host records in; pinned host 2-byte token ids, rows back to back, "
-                       "+ int32 lengths out; exact-size copies)",
+                "d2h_bytes_per_step": int(2 * e2e_tokens_all + 12 * world * n_e2e), "records_per_step": world * n_e2e, "steps": e2e_steps,
+                "api": "ecgbyte.api.EncodePipelineCSR.run (pinned host records in; 2-byte token ids stored by the kernel straight "
+                       "into pinned host memory, + int64 offsets and int32 lengths; consecutive steps pipeline into each other)",
                 "copy_ceiling": {"h2d_gbs_all_ranks": h2d_sum, "d2h_gbs_all_ranks": d2h_sum,
                                  "h2d_plus_d2h_concurrent_s": t_both, "records_per_s": ceiling,
                                  "what": "bare pinned cudaMemcpyAsync of the same buffers on %d rank(s) at once, no kernels" % world},
@@ -512,7 +512,7 @@ def run_ours(args, rank, world, local_rank):
     if e2e_i16_ms is not None:
         i16_value = world * n_e2e * e2e_steps / (e2e_i16_ms * 1e-3)
         line["e2e_int16"] = {"value": i16_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n_e2e * REC_LEN * 2),
-                             "d2h_bytes_per_step": int(2 * e2e_tokens_all + 4 * world * n_e2e),
+                             "d2h_bytes_per_step": int(2 * e2e_tokens_all + 12 * world * n_e2e),
                              "what": "the same pipeline fed int16 records (1 uV/LSB, PTB-XL's storage type)",
                              "frac_of_copy_ceiling": i16_value / (h2d_sum * 1e9 / (REC_LEN * 2))}
     print(json.dumps(line), flush=True)

@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(256) token_hist_kernel(const int32_t *__restri
 // The encoder writes int32 rows of out_stride slots; what a host consumer needs is the tokens themselves:
 // 2-byte ids (< 65 536 by construction), rows back to back.  One CTA scans the lengths, all CTAs copy.
 __global__ void __launch_bounds__(1024) csr_offsets_kernel(const int32_t *__restrict__ len, size_t n_rec, size_t in_stride,
-                                                           unsigned long long *__restrict__ off) {
+                                                           unsigned long long *__restrict__ off, unsigned long long base) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_base;
-    if (threadIdx.x == 0) s_base = 0;
+    if (threadIdx.x == 0) s_base = base;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (size_t c0 = 0; c0 < n_rec; c0 += 1024) {
@@ -342,16 +342,19 @@ extern "C" int ecgb_pack_training(const int32_t *d_tokens, size_t in_stride, con
 }
 
 // Compact copy of the encoder's output: rows of 2-byte token ids back to back (CSR).  d_off[n_rec + 1] receives
-// the row offsets in tokens (d_off[n_rec] = total); d_out needs room for sum(min(len, in_stride)) tokens.
+// the row offsets in tokens, counted from `base` (d_off[n_rec] = base + total); row r goes to out[d_off[r] ...], so
+// `out` needs room for base + sum(min(len, in_stride)) tokens.  `out` may be PINNED HOST memory (mapped into the
+// device's address space, as cudaHostAlloc / torch pin_memory() memory is): the copy kernel then stores the tokens
+// straight over PCIe and no host-side size hand-over is needed.
 extern "C" int ecgb_tokens_csr(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec, uint16_t *d_out,
-                               uint64_t *d_off, int device, void *stream) {
+                               uint64_t *d_off, uint64_t base, int device, void *stream) {
     ECGB_REQUIRE(d_off, "d_off is NULL");
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
     cudaStream_t st = as_stream(stream);
     ECGB_REQUIRE(n_rec == 0 || (d_tokens && d_len && d_out), "NULL buffer");
-    csr_offsets_kernel<<<1, 1024, 0, st>>>(d_len, n_rec, in_stride, reinterpret_cast<unsigned long long *>(d_off));
+    csr_offsets_kernel<<<1, 1024, 0, st>>>(d_len, n_rec, in_stride, reinterpret_cast<unsigned long long *>(d_off), (unsigned long long)base);
     if (n_rec) {
         const unsigned grid = (unsigned)std::min<size_t>(n_rec, (size_t)sm_count(device) * 8);
         csr_copy_kernel<<<grid, 256, 0, st>>>(d_tokens, in_stride, d_len, n_rec, reinterpret_cast<const unsigned long long *>(d_off), d_out);

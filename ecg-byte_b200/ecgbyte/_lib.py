@@ -57,7 +57,7 @@ def _declare(L):
         "ecgb_decode_symbols": ([vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
         "ecgb_dequantize": ([dbl, dbl, vp, sz, vp, i32, vp], i32),
         "ecgb_expand_attention": ([vp, vp, vp, sz, sz, vp, vp, sz, vp, vp], i32),
-        "ecgb_tokens_csr": ([vp, sz, vp, sz, vp, vp, i32, vp], i32),
+        "ecgb_tokens_csr": ([vp, sz, vp, sz, vp, vp, u64, i32, vp], i32),
         "ecgb_token_histogram": ([vp, sz, vp, sz, u32, vp, i32, vp], i32),
         "ecgb_minmax": ([vp, i32, sz, C.POINTER(dbl), C.POINTER(dbl), i32, vp], i32),
         "ecgb_percentiles": ([vp, sz, vp, i32, vp, i32, vp], i32),

@@ -330,12 +330,19 @@ class EncodePipeline:
         self.d_tok = [torch.empty((chunk, out_stride), dtype=torch.int32, device=dev) for _ in range(depth)]
         self.d_len = [torch.empty((chunk,), dtype=torch.int32, device=dev) for _ in range(depth)]
 
-    def run(self, x_pinned, tokens_pinned, lens_pinned):
+    def run(self, x_pinned, tokens_pinned, lens_pinned, after_current_stream=False):
+        """Enqueues the whole batch and returns; the caller's current stream waits for the results (synchronise it, or
+        record an event on it, before reading the pinned outputs).  Consecutive calls pipeline into each other: the
+        first chunks of the next batch are copied in while the last chunks of this one are still being encoded and
+        copied out (a chunk's kernel has a latency floor of several ms -- one walker per record -- which would
+        otherwise be paid as a drain at the end of every call).  after_current_stream=True orders the batch behind
+        work already enqueued on the current stream (inputs produced on the device side)."""
         n = x_pinned.shape[0]
         x2 = x_pinned.view(n, self.rec_len)
         cur = torch.cuda.current_stream(self.dev)
-        for s in self.streams:
-            s.wait_stream(cur)
+        if after_current_stream:
+            for s in self.streams:
+                s.wait_stream(cur)
         k = 0
         for c0 in range(0, n, self.chunk):
             m = min(self.chunk, n - c0)
@@ -353,64 +360,50 @@ class EncodePipeline:
 
 
 class EncodePipelineCSR(EncodePipeline):
-    """EncodePipeline with compact output: what crosses PCIe on the way back is 2 bytes per token plus 4 bytes per
-    record (lengths), instead of a padded int32 row of out_stride slots.  Record r's tokens are
-    tokens16[off[r]:off[r + 1]] with off = concatenate([0], cumsum(lens)) (records in input order).
+    """EncodePipeline with compact output: what crosses PCIe on the way back is 2 bytes per token plus 12 bytes per
+    record (offset, length) instead of a padded int32 row of out_stride slots.  Record r's tokens are
+    tokens16[off[r] : off[r] + lens[r]]; rows are back to back inside a chunk of `chunk` records, and chunk k starts at
+    k * chunk * out_stride (no size has to travel to the host before the data does).
 
-    The exact byte count of a chunk is only known on the device, so its token copy is issued late: while chunk k's
-    input is in flight the host reads the total of chunk k - (depth - 1) (an 8-byte copy that finished long before)
-    and enqueues exactly that many bytes -- no padding is transferred and the host never waits."""
+    The compaction kernel stores the tokens STRAIGHT into the pinned host buffer (pinned memory is mapped into the
+    device's address space), so there is no device-to-host token copy to size and no host synchronisation anywhere in
+    the pipeline."""
 
     def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
         super().__init__(vocab, quantizer, rec_len, out_stride, chunk, depth)
-        dev = self.dev
-        self.d_tok16 = [torch.empty((chunk * out_stride,), dtype=torch.uint16, device=dev) for _ in range(depth)]
-        self.d_off = [torch.empty((chunk + 1,), dtype=torch.int64, device=dev) for _ in range(depth)]
-        self.h_tot = [torch.zeros((1,), dtype=torch.int64).pin_memory() for _ in range(depth)]
-        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.d_off = [torch.empty((chunk + 1,), dtype=torch.int64, device=self.dev) for _ in range(depth)]
 
-    def run(self, x_pinned, tokens16_pinned, lens_pinned):
-        """tokens16_pinned: flat pinned uint16 buffer with room for every token; returns (launches, total tokens)."""
+    def run(self, x_pinned, tokens16_pinned, lens_pinned, off_pinned, after_current_stream=False):
+        """tokens16_pinned: flat pinned uint16 buffer of n * out_stride slots; lens_pinned int32 [n]; off_pinned int64 [n].
+        Stream semantics as EncodePipeline.run (consecutive calls pipeline into each other).  Returns the number of
+        kernel launches."""
         n = x_pinned.shape[0]
+        if tokens16_pinned.numel() < n * self.out_stride:
+            raise ValueError("tokens16 buffer needs n * out_stride slots")
+        if not (tokens16_pinned.is_pinned() and lens_pinned.is_pinned() and off_pinned.is_pinned()):
+            raise ValueError("outputs must be pinned host tensors")
         x2 = x_pinned.view(n, self.rec_len)
         cur = torch.cuda.current_stream(self.dev)
-        for s in self.streams:
-            s.wait_stream(cur)
-        chunks = [(c0, min(self.chunk, n - c0)) for c0 in range(0, n, self.chunk)]
-        base = 0
-        # a chunk's token copy is issued `lag` chunks late (its kernels finished long before, so reading its total never
-        # blocks the host); its slot is reused `depth` chunks later, on the same stream, i.e. behind that copy
-        lag = max(1, self.depth - 1)
-
-        def finish(k):  # chunk k's tokens: exact size, behind its own kernels on its own stream
-            nonlocal base
+        if after_current_stream:
+            for s in self.streams:
+                s.wait_stream(cur)
+        k = 0
+        for c0 in range(0, n, self.chunk):
+            m = min(self.chunk, n - c0)
             b = k % self.depth
-            self.ev[b].synchronize()
-            tot = int(self.h_tot[b][0])
-            if base + tot > tokens16_pinned.numel():
-                raise ValueError("tokens16 buffer too small")
-            with torch.cuda.stream(self.streams[b]):
-                tokens16_pinned[base:base + tot].copy_(self.d_tok16[b][:tot], non_blocking=True)
-            base += tot
-
-        for k, (c0, m) in enumerate(chunks):
-            b = k % self.depth
+            k += 1
             with torch.cuda.stream(self.streams[b]):
                 self.d_in[b][:m].copy_(x2[c0:c0 + m], non_blocking=True)
                 self.vocab.encode_batch(self.q, self.d_in[b][:m], out_stride=self.out_stride,
                                         tokens=self.d_tok[b], lens=self.d_len[b])
-                check(lib().ecgb_tokens_csr(_ptr(self.d_tok[b]), self.out_stride, _ptr(self.d_len[b]), m, _ptr(self.d_tok16[b]),
-                                            _ptr(self.d_off[b]), self.dev.index, _stream(self.dev)))
-                self.h_tot[b].copy_(self.d_off[b][m:m + 1], non_blocking=True)
+                check(lib().ecgb_tokens_csr(_ptr(self.d_tok[b]), self.out_stride, _ptr(self.d_len[b]), m,
+                                            _ptr(tokens16_pinned), _ptr(self.d_off[b]), c0 * self.out_stride,
+                                            self.dev.index, _stream(self.dev)))
+                off_pinned[c0:c0 + m].copy_(self.d_off[b][:m], non_blocking=True)
                 lens_pinned[c0:c0 + m].copy_(self.d_len[b][:m], non_blocking=True)
-                self.ev[b].record()
-            if k >= lag:
-                finish(k - lag)
-        for k in range(max(len(chunks) - lag, 0), len(chunks)):
-            finish(k)
         for s in self.streams:
             cur.wait_stream(s)
-        return 3 * len(chunks), base
+        return 3 * k
 
 
 def expand_merges(pairs):

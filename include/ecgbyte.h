@@ -161,9 +161,10 @@ int ecgb_expand_attention(const ecgb_vocab *v, const int32_t *d_tokens, const fl
                           int32_t *d_out_len, void *stream);
 /* Compact (CSR) copy of the encoder's output for host consumers of ecgb_encode_batch (the list[int] that
  * rust_bpe.encode_text returns, lib.rs:192, per record): 2-byte ids (ids < 65 536), rows back to back.
- * d_off[n_rec + 1] = row offsets in tokens, d_off[n_rec] = total; d_out holds sum(min(len, in_stride)). */
-int ecgb_tokens_csr(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec, uint16_t *d_out,
-                    uint64_t *d_off, int device, void *stream);
+ * d_off[n_rec + 1] = row offsets in tokens counted from `base`, d_off[n_rec] = base + total; row r is written to
+ * out[d_off[r] ...].  `out` may be pinned (mapped) host memory: the kernel then stores straight over PCIe. */
+int ecgb_tokens_csr(const int32_t *d_tokens, size_t in_stride, const int32_t *d_len, size_t n_rec, uint16_t *out,
+                    uint64_t *d_off, uint64_t base, int device, void *stream);
 /* analyze_token_distribution (tokenizer_utils.py:30-54): Counter over the encoded ids of a batch.
  * d_counts[n_ids] (u64, device) is ACCUMULATED into -- zero it first; the per-record token_lengths
  * of the reference are the encoder's d_len.  An id outside [0, n_ids) is ECGB_EINVAL. */

@@ -220,8 +220,8 @@ def test_token_histogram_matches_counter(tmp_path):
 
 
 def test_encode_pipeline_csr(oracle, small_corpus, small_table):
-    """Host-buffer pipeline with compact output (2-byte ids, rows back to back, exact-size copies) == oracle,
-    over several chunks, and == the padded int32 pipeline."""
+    """Host-buffer pipeline with compact output (2-byte ids stored by the kernel straight into pinned host memory, rows
+    back to back inside a chunk) == oracle, over several chunks and two pipelined calls, and == the padded int32 pipeline."""
     from ecgbyte.api import EncodePipeline, EncodePipelineCSR, Quantizer, Vocab
     x, pct = small_corpus
     _, vocab, merges = small_table
@@ -233,21 +233,27 @@ def test_encode_pipeline_csr(oracle, small_corpus, small_table):
     xh = torch.from_numpy(x.astype(np.float32)).pin_memory()
     tok16 = torch.zeros(n * stride, dtype=torch.uint16).pin_memory()
     lens = torch.zeros(n, dtype=torch.int32).pin_memory()
+    offp = torch.zeros(n, dtype=torch.int64).pin_memory()
     pipe = EncodePipelineCSR(v, q, rec_len, stride, chunk=3, depth=2)   # ragged last chunk, slots reused
-    launches, total = pipe.run(xh, tok16, lens)
+    for _ in range(2):                                                  # consecutive calls pipeline into each other
+        pipe.run(xh, tok16, lens, offp)
     torch.cuda.synchronize()
-    assert total == int(lens.sum())
-    off = np.concatenate([[0], np.cumsum(lens.numpy().astype(np.int64))])
+    off = offp.numpy()
     trie = oracle.Trie(merges=merges)
     t16 = tok16.numpy()
+    want_off = 0
     for r in range(n):
+        if r % 3 == 0:
+            want_off = r * stride                                        # chunk starts at a fixed place
+        assert off[r] == want_off                                        # rows back to back inside the chunk
         sym = oracle.quantize(x[r].astype(np.float32), pct["percentile_1"], pct["percentile_99"]).reshape(-1)
         want = trie.encode(sym)
-        np.testing.assert_array_equal(t16[off[r]:off[r + 1]].astype(np.uint32), want.astype(np.uint32))
+        np.testing.assert_array_equal(t16[off[r]:off[r] + lens[r]].astype(np.uint32), want.astype(np.uint32))
+        want_off += len(want)
     tok32 = torch.zeros((n, stride), dtype=torch.int32).pin_memory()
     lens2 = torch.zeros(n, dtype=torch.int32).pin_memory()
     EncodePipeline(v, q, rec_len, stride, chunk=3, depth=2).run(xh, tok32, lens2)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(lens.numpy(), lens2.numpy())
     for r in range(n):
-        np.testing.assert_array_equal(t16[off[r]:off[r + 1]].astype(np.int32), tok32[r, : lens2[r]].numpy())
+        np.testing.assert_array_equal(t16[off[r]:off[r] + lens[r]].astype(np.int32), tok32[r, : lens2[r]].numpy())
