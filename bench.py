@@ -299,6 +299,16 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     k1_ms = float(np.mean(timed(lambda: q.quantize(x, out=sym_out), 5, dev, torch)))
     k1_bytes = n_rec * REC_LEN * (4 + 1)
+    # every record of the timed batch, on the device: the tokens of the fused kernel decode (decode_text, tu.py:75-77)
+    # back to exactly the symbols quantize_kernel produces -- K1 and K1-inside-K2 agree and no token is lost or misplaced
+    roundtrip_ok = True
+    for a in range(0, n_rec, 25000):
+        b = min(n_rec, a + 25000)
+        dec, dec_len = v.decode_symbols(tokens[a:b], lens[a:b], REC_LEN)
+        roundtrip_ok = roundtrip_ok and bool((dec_len == REC_LEN).all()) and bool(torch.equal(dec, sym_out[a:b]))
+        del dec, dec_len
+    if not roundtrip_ok:
+        raise SystemExit("bench.py: PARITY FAILURE (decode(encode(record)) != quantize(record) for some record) -- numbers withheld")
     # spot check of K1 on the timed batch
     from oracle import oracle as O
     k1_idx = [0, n_rec // 2, n_rec - 1]
@@ -507,7 +517,9 @@ def run_ours(args, rank, world, local_rank):
         "config3": cfg3,
         "train": train,
         "clocks": clocks,
-        "parity": {"records_checked": int(len(idx)), "ok": True},
+        "parity": {"records_checked": int(len(idx)), "ok": True,
+                   "what": "tokens of %d records of the timed batch == oracle; all %d records: decode(tokens) == quantize_kernel symbols "
+                           "(device-side round trip); e2e tokens == resident tokens; K1 symbols, merge lists == oracle" % (len(idx), n_rec)},
     }
     if e2e_i16_ms is not None:
         i16_value = world * n_e2e * e2e_steps / (e2e_i16_ms * 1e-3)

@@ -48,6 +48,7 @@ constexpr int kTile = kTPB * kIPT;
 constexpr int kBoundaryWords = 16;       // u32 words of boundary info per rank
 constexpr int kCtasPerSm = 4;            // co-resident CTAs per SM of the persistent kernels (launch bounds)
 constexpr int kMaxWorld = 16;            // ranks of one sharded run (the GPUs of one box)
+constexpr int kApplyCtas = 16;           // persistent sharded loop: CTAs that apply one peer's patch list
 constexpr uint32_t kRedundantArgmax = 2048;  // candidate lists up to this size are scanned by every CTA
 constexpr int kChunkTiles = 3;           // resident tail: each CTA keeps up to 3 tiles of the stream in shared memory
 constexpr int kChunkCap = kChunkTiles * kTile;
@@ -1483,24 +1484,25 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
             if (lane < pv.world && lane != pv.rank)  // lane r serves peer r: the step's flag with the list length
                 st_unit(pv.area[lane] + peer_flag_off(pv.world, par, pv.rank), cnt, peer_tag(pv.epoch, step));
         }
-        // the peers' patches of this step
-        if (threadIdx.x < (unsigned)pv.world) {
-            uint32_t cnt = 0;
-            if ((int)threadIdx.x != pv.rank)
-                cnt = wait_unit(mine + peer_flag_off(pv.world, par, (int)threadIdx.x), peer_tag(pv.epoch, step), abort, pv.timeout_ns,
-                                (2u << 28) | (threadIdx.x << 20) | (step & 0xFFFFFu));
-            sm.peer_cnt[threadIdx.x] = min(cnt, pv.cap);
-        }
-        __syncthreads();
-        ECGB_MARK(12);
+        // the peers' patches of this step: kApplyCtas CTAs per peer wait for that peer's flag and apply its list, the
+        // other CTAs go straight to the barrier (every CTA polling every peer's flag -- thousands of threads spinning on
+        // a handful of words that NVLink writes have yet to land in -- was measurably slower)
         {
-            const unsigned long long tau_val = sm.tau_val;  // read by the pass; tau only changes inside the argmax
-            const uint32_t tag = peer_tag(pv.epoch, step);
-            for (int r = 0; r < pv.world; r++) {
-                if (r == pv.rank) continue;
-                const uint32_t cnt = sm.peer_cnt[r];
+            const int n_peers = pv.world - 1;
+            const int per_peer = max(1, min(kApplyCtas, (int)gridDim.x / max(n_peers, 1)));
+            const int slot = (int)blockIdx.x / per_peer, sub = (int)blockIdx.x % per_peer;  // which peer, which share of its list
+            if (slot < n_peers) {
+                const int r = slot < pv.rank ? slot : slot + 1;
+                if (threadIdx.x == 0)
+                    sm.peer_cnt[0] = min(wait_unit(mine + peer_flag_off(pv.world, par, r), peer_tag(pv.epoch, step), abort, pv.timeout_ns,
+                                                   (2u << 28) | ((uint32_t)r << 20) | (step & 0xFFFFFu)), pv.cap);
+                __syncthreads();
+                ECGB_MARK(12);
+                const unsigned long long tau_val = sm.tau_val;  // read by the pass; tau only changes inside the argmax
+                const uint32_t tag = peer_tag(pv.epoch, step);
+                const uint32_t cnt = sm.peer_cnt[0];
                 const uint4 *ent = reinterpret_cast<const uint4 *>(mine + peer_ent_off(pv.world, pv.cap, par, r));
-                for (uint64_t i = gtid; i < cnt; i += gthreads) {
+                for (uint32_t i = (uint32_t)sub * kTPB + threadIdx.x; i < cnt; i += (uint32_t)per_peer * kTPB) {
                     // an entry may still be in flight behind the flag: both halves carry the tag
                     uint4 e;
                     unsigned long long t0 = 0;
