@@ -5,20 +5,22 @@
 // as symbols match, remember the longest terminal seen, emit it and restart right
 // after it (lib.rs:163-190).  This is NOT rank-ordered BPE merging.
 //
-// Mapping (one walker = one thread = one record, 1 CTA of up to 1024 walkers per SM):
-//   * records are independent and 100k-1M of them are in flight, so the
-//     record axis alone fills the chip: no speculation, no redundant trie steps, no
-//     inter-thread synchronisation after the tables are staged;
-//   * the trie (8-byte bitmap nodes, ~90 KB for 5,000 merges) is staged once per CTA in
-//     shared memory; one trie step = one LDS.64 + popc;
-//   * each walker streams its own record from HBM with 128-bit loads, one 32-byte sector
-//     (8 fp32 samples) per request, prefetched one group ahead in registers; samples are
-//     quantised by threshold classification as they arrive and kept as a 16-symbol
-//     register window, so symbols never touch HBM or shared memory;
-//   * a failed walk re-reads the symbols after the emitted token from the window
-//     (99.3 % of restarts reach back <= 8 symbols on ECG data); a longer reach-back
-//     re-primes the window from L1/L2.
-// HBM traffic is therefore the algorithmic minimum: samples once, tokens once.
+// Mapping (one walker = one thread = one record, 1 CTA of up to 768 walkers per SM, 85 registers each):
+//   * records are independent and 100k-1M of them are in flight, so the record axis alone fills
+//     the chip: no speculation, no redundant trie steps, no inter-thread synchronisation after the tables are staged;
+//   * the trie (8-byte bitmap nodes, 104 KB for 5,000 merges) is staged once per CTA in shared memory (nodes
+//     that do not fit stay in L2; tables that spill go to the pair-table walker of encode2.cu instead);
+//   * a warp alternates between two CONVERGENT phases.  Refill: every lane with room loads 16 samples of its own
+//     record (4 x LDG.128), classifies them (K1's arithmetic, quant_device.cuh) and appends 16 shift codes to its
+//     private 128-symbol ring in shared memory; rings are transposed per warp (word w of lane l at (w * 32 + l) * 4),
+//     so ring traffic is conflict-free wherever each cursor is.  Walk: K = REDUX.MIN(symbols left in the rings)
+//     branch-free trie steps -- one LDS.U8 (symbol, loaded one step ahead), one LDS.64 (node), a sign test and a
+//     POPC per step, predicated token store; the end of a record is a sentinel symbol that has no edge;
+//   * a failed walk restarts right after the emitted token at a ring position that is still there (the ring never
+//     drops symbols after the last terminal); the rare walk longer than the ring finishes symbol by symbol from
+//     global memory.
+// HBM traffic is the algorithmic minimum: samples once, tokens once (ncu: 270.7 KB per record against 258.3 KB).
+// Measured history and the limits of this design: DESIGN.md section 4, K2.
 #include <algorithm>
 #include <cstring>
 
