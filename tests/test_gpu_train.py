@@ -216,3 +216,19 @@ def test_persistent_sharded_loop_streaming_then_resident(oracle):
     n = sym.size  # 360 000 symbols; 2 CTAs x 12 288 resident tokens per rank
     _check_persistent(oracle, sym, [n // 2 - 7], 120, max_ctas=2)
     _check_persistent(oracle, sym, [n // 5, n // 2], 120, max_ctas=3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CUDA IPC between one-process-per-GPU ranks)")
+@pytest.mark.parametrize("mode", ["persistent", "auto"])
+def test_sharded_training_real_ranks(mode):
+    """tests/dist_gpu_train.py under torchrun on two GPUs: dist_loop_kernel with the peers' areas mapped through CUDA
+    IPC (persistent) and the public auto policy; merge list, counts, tie log and merged stream == oracle."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(here, "dist_gpu_train.py"), "40", "300", mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PARITY OK" in out.stdout
