@@ -743,7 +743,10 @@ __device__ __forceinline__ void merge_pass(const TrainView &v, uint32_t step, co
             tile = sm.tile;
         } else {
             tile = resident ? round : (long long)blockIdx.x + round * (long long)gridDim.x;
-            __syncthreads();  // shared staging of the previous tile is free again
+            // Chunks: no barrier between tiles.  What the next tile overwrites first is sm.in, which the previous tile
+            // stopped reading before its last barrier (the write-out reads sm.out only); sm.out is written again two
+            // barriers into the next tile; the in-place write-out ends where the next tile's loads begin.
+            if (!resident) __syncthreads();  // shared staging of the previous tile is free again
         }
         if (tile >= ntiles) break;
         const long long tbase = tile * kTile;
