@@ -326,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
     tok16_h = torch.empty((n_e2e * stride,), dtype=torch.uint16).pin_memory()
     len_h = torch.empty((n_e2e,), dtype=torch.int32).pin_memory()
     off_h = torch.empty((n_e2e,), dtype=torch.int64).pin_memory()
-    pipe = EncodePipelineCSR(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
+    pipe = EncodePipelineCSR(v, q, REC_LEN, stride, chunk=args.e2e_chunk, depth=args.e2e_depth)
     e2e_steps = max(3, min(args.steps, 5))
 
     def time_pipe(p, xin, *outs):
@@ -355,13 +355,13 @@ def run_ours(args, rank, world, local_rank):
         x16 = torch.clamp(torch.round(x[:n_e2e] * 1000.0), -32768, 32767).to(torch.int16)
         xh16 = torch.empty((n_e2e, C_LEADS, L_SAMPLES), dtype=torch.int16).pin_memory()
         xh16.copy_(x16)
-        pipe16 = EncodePipelineCSR(v, q16, REC_LEN, stride, chunk=args.e2e_chunk)
+        pipe16 = EncodePipelineCSR(v, q16, REC_LEN, stride, chunk=args.e2e_chunk, depth=args.e2e_depth)
         e2e_i16_ms, _ = time_pipe(pipe16, xh16, tok16_h, len_h, off_h)
         del x16, pipe16
 
     # padded int32 rows (round-1 output format), for comparison
     tok32_h = torch.empty((n_e2e, stride), dtype=torch.int32).pin_memory()
-    pipe32 = EncodePipeline(v, q, REC_LEN, stride, chunk=args.e2e_chunk)
+    pipe32 = EncodePipeline(v, q, REC_LEN, stride, chunk=args.e2e_chunk, depth=args.e2e_depth)
     e2e32_ms, _ = time_pipe(pipe32, xh, tok32_h, len_h)
     del pipe32
 
@@ -742,6 +742,7 @@ def main():
     ap.add_argument("--out-stride", type=int, default=8192)
     ap.add_argument("--e2e-records", type=int, default=16384)
     ap.add_argument("--e2e-chunk", type=int, default=2048)
+    ap.add_argument("--e2e-depth", type=int, default=4, help="chunks in flight in the end-to-end pipeline")
     ap.add_argument("--check", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")

@@ -320,7 +320,7 @@ class EncodePipeline:
     so the H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1
     overlap (the path is PCIe-bound: 240 KB in per fp32 record)."""
 
-    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
+    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=4):
         self.vocab, self.q = vocab, quantizer
         self.rec_len, self.out_stride, self.chunk, self.depth = rec_len, out_stride, chunk, depth
         dev = torch.device("cuda", vocab.device)
@@ -369,7 +369,7 @@ class EncodePipelineCSR(EncodePipeline):
     device's address space), so there is no device-to-host token copy to size and no host synchronisation anywhere in
     the pipeline."""
 
-    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=3):
+    def __init__(self, vocab, quantizer, rec_len, out_stride, chunk=4096, depth=4):
         super().__init__(vocab, quantizer, rec_len, out_stride, chunk, depth)
         self.d_off = [torch.empty((chunk + 1,), dtype=torch.int64, device=self.dev) for _ in range(depth)]
 
