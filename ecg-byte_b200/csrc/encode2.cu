@@ -50,8 +50,23 @@
 #ifndef ECGB_ENC_MAXB
 #define ECGB_ENC_MAXB 8
 #endif
+#ifndef ECGB_ENC_MINLANES
+#define ECGB_ENC_MINLANES 20  // a refill round that fewer lanes want is put off unless one of them is short of symbols
+#endif
+#ifndef ECGB_ENC_NEEDY
+#define ECGB_ENC_NEEDY 24     // "short of symbols": fewer than this many ahead of the cursor
+#endif
 
 namespace ecgb {
+
+#ifdef ECGB_ENC_STATS
+// instrumentation (profiles only): [0..8] walk phases by K, [16..48] refill rounds by lanes wanting,
+// [50] rewinds, [51] failure blocks, [52] lanes served in failure blocks, [53] bursts, [54] lanes still running at burst end
+__device__ unsigned long long g_enc_stats[64];
+#define ENC_STAT(i, v) do { if (threadIdx.x == 0 && (blockIdx.x & 7u) == 0) atomicAdd(&g_enc_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define ENC_STAT(i, v) do { } while (0)
+#endif
 
 struct Enc2Args {
     const void *in;            // samples (or text bytes), all records back to back
@@ -365,7 +380,23 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
             const bool room = hi32 - max(mq >> 1, (q >> 1) - kHist) <= kRing2 - kG2 - 2;
             const bool starved = hi32 - (q >> 1) < 2 * kBurst;
             const bool want = active && !closed && (room || starved);
-            if (!__any_sync(FULL, want)) break;
+            // A round costs the same whether one lane or all of them take part, and every lane needs 1 group per 16
+            // symbols it consumes whatever the schedule: rounds that only a few lanes want (a lane whose consumption has
+            // just crossed a multiple of 16) are put off until they fill up -- unless such a lane is running dry, which
+            // would cut the next walk phase short for the whole warp.
+            {
+                const unsigned wm = __ballot_sync(FULL, want);
+                if (!wm) break;
+                const bool needy = want && (hi32 - (q >> 1) < ECGB_ENC_NEEDY);
+#ifdef ECGB_ENC_NEEDY_FIRST_ROUND_ONLY
+                if (__popc(wm) < ECGB_ENC_MINLANES && (g > 0 || !__any_sync(FULL, needy))) break;
+#else
+                if (__popc(wm) < ECGB_ENC_MINLANES && !__any_sync(FULL, needy)) break;
+#endif
+            }
+#ifdef ECGB_ENC_STATS
+            { const int nw_ = __popc(__ballot_sync(FULL, want)); ENC_STAT(16 + nw_, 1); }
+#endif
             if (want) {
                 refill16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, al32, ring_lane, hi32, prev, wmul, se4, qlo,
                                     qscale, cell_sa, s_thr, cls_sa);
@@ -383,6 +414,7 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
         uint32_t nb = 0x7fffffffu;
         if (active && !closed) nb = (uint32_t)(hi32 - (q >> 1)) / (2u * kBurst);
         uint32_t K = min(__reduce_min_sync(FULL, nb), (uint32_t)kMaxBursts);
+        ENC_STAT(K, 1);
         ra = ring_at2(ring_lane, q + 2);
         cw = lds16(ra);
         bool walk = active;
@@ -399,6 +431,10 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
                 run = ok;
             }
             const bool f = walk && !run;
+#ifdef ECGB_ENC_STATS
+            { const int nr_ = __popc(__ballot_sync(FULL, run)), nf_ = __popc(__ballot_sync(FULL, f));
+              ENC_STAT(53, 1); ENC_STAT(54, nr_); if (nf_) { ENC_STAT(51, 1); ENC_STAT(52, nf_); } }
+#endif
             if (__any_sync(FULL, f)) {
                 if (f) {
                     // the pair at the cursor is no edge: the first symbol alone may still reach a token
@@ -421,6 +457,9 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
                         if ((nq >> 1) + 1 < hi32 - kRing2) {  // the restart point has left the ring
                             parked = rewind = true;
                             walk = false;
+#ifdef ECGB_ENC_STATS
+                            if ((blockIdx.x & 7u) == 0 && threadIdx.x < 32) atomicAdd(&g_enc_stats[50], 1ull);
+#endif
                         } else {
                             ra = ring_at2(ring_lane, q + 2);
                             cw = lds16(ra);
@@ -474,6 +513,20 @@ static int launch_encode2_t(const Enc2Args &a, int exact_cells, int device, cuda
     ECGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, (unsigned)(w * 32), smem, st>>>(a);
     ECGB_CUDA(cudaGetLastError());
+#ifdef ECGB_ENC_STATS
+    {
+        unsigned long long h[64], z[64] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_enc_stats, sizeof(h));
+        cudaMemcpyToSymbol(g_enc_stats, z, sizeof(z));
+        fprintf(stderr, "enc2 stats: K:");
+        for (int i = 0; i <= 8; i++) fprintf(stderr, " %llu", h[i]);
+        fprintf(stderr, "\n  refill rounds by lanes wanting (1..32):");
+        for (int i = 1; i <= 32; i++) fprintf(stderr, " %llu", h[16 + i]);
+        fprintf(stderr, "\n  rewinds %llu, failure blocks %llu serving %llu lanes, bursts %llu with %llu lanes still running at the end\n",
+                h[50], h[51], h[52], h[53], h[54]);
+    }
+#endif
     return ECGB_OK;
 }
 
@@ -485,17 +538,22 @@ int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact
                    int32_t *d_len, int device, cudaStream_t st) {
     if (!vv->pair.d_ent) return ECGB_EUNSUPPORTED;
     if (rec_len >= (1ull << 30)) return ECGB_EUNSUPPORTED;
-    // Which walker: measured on B200 (100 k records), the two-symbol-stride walker equals the bitmap-trie kernel while
-    // that kernel's whole trie sits in shared memory (5 000 merges: 13.96 vs 13.91 ms) and beats it once the trie
-    // spills to L2 (10 000 merges: 21.7 vs 27.4 ms) -- the pair table is 2.6x smaller.  So: this kernel when the
-    // 8-byte nodes do not fit next to 768 walkers' rings.  A/B knobs: ECGB_ENCODE_V1 / ECGB_ENCODE_V2 force one.
+    // Which walker (measured on B200, profiles/encode_ab.py, profiles/encode_cases.py):
+    //   * the 8-byte trie does not fit in shared memory next to 768 walkers' rings (10 000 merges): this kernel, whose
+    //     pair table is 2.6x smaller -- 14.3 ms against 27.4 ms for 100 k records;
+    //   * the trie fits and the batch fills the chip (>= 512 records per SM): this kernel -- 13.3 against 13.9 ms (fp32),
+    //     13.0 against 13.3 (int16), 6.67 against 7.00 (12 x 2500);
+    //   * smaller batches: the bitmap kernel, whose step chain is shorter -- a launch is then as long as ONE record's walk
+    //     (2 048 records: 8.0 against 9.5 ms; 2 records of 12 x 500: 0.54 against 0.63 ms).
+    // A/B knobs: ECGB_ENCODE_V1 / ECGB_ENCODE_V2 force one.
     static const bool force_v1 = getenv("ECGB_ENCODE_V1") != nullptr, force_v2 = getenv("ECGB_ENCODE_V2") != nullptr;
     if (force_v1) return ECGB_EUNSUPPORTED;
     if (!force_v2) {
         int smem_max = 0;
         ECGB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         const size_t trie_and_rings = (size_t)vv->n_nodes * 8 + 768 * 128 + 4096;
-        if (trie_and_rings <= (size_t)smem_max) return ECGB_EUNSUPPORTED;
+        const bool trie_fits = trie_and_rings <= (size_t)smem_max;
+        if (trie_fits && n_rec < (size_t)512 * (size_t)sm_count(device)) return ECGB_EUNSUPPORTED;
     }
     Enc2Args a{};
     a.in = d_in; a.n_total = n_total; a.n_rec = n_rec; a.rec_len = rec_len; a.offsets = d_offsets;

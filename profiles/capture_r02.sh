@@ -13,7 +13,11 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --no-cpu --no-config4 --e2e-records 4096 > gpurun_out/launches_r02.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode_kernel -s 3 -c 1 \
     -o gpurun_out/encode_r02 -f \
-    python bench.py --steps 1 --warmup 3 --no-cpu --no-train --no-config3 --no-i16 --e2e-records 2048 > gpurun_out/encode_r02.log 2>&1
+    env ECGB_ENCODE_V1=1 python bench.py --steps 1 --warmup 3 --no-cpu --no-train --no-config3 --no-i16 --e2e-records 2048 > gpurun_out/encode_r02.log 2>&1
+# the headline kernel of the final build: the pair-table walker on the 5,000-merge table
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode2_kernel -s 3 -c 1 \
+    -o gpurun_out/encode2_r02_final -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-train --no-config3 --no-i16 --e2e-records 2048 > gpurun_out/encode2_r02_final.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode2_kernel -s 3 -c 1 \
     -o gpurun_out/encode2_r02 -f \
     python profiles/encode_ab.py 100000 10000 f32 > gpurun_out/encode2_r02.log 2>&1
