@@ -56,6 +56,14 @@ template <int DT> struct ThrOf { using T = typename SampleTraits<DT>::Thr; };
 template <> struct ThrOf<ECGB_U8> { using T = float; };
 
 constexpr int kGroup = 16;
+#ifndef ECGB_ENC1_MINLANES
+#define ECGB_ENC1_MINLANES 20
+#endif
+#ifndef ECGB_ENC1_NEEDY
+#define ECGB_ENC1_NEEDY 48
+#endif
+constexpr int kMinRefillLanes = ECGB_ENC1_MINLANES;  // refill rounds wanted by fewer lanes wait ...
+constexpr int kNeedySymbols = ECGB_ENC1_NEEDY;       // ... unless a lane has fewer symbols than this ahead of its cursor
 constexpr int kMaxThreads = 768;  // walkers per CTA: 85 registers each, 24 warps per SM
 
 // 16 samples at global index g (g % 16 == 0) -> 16 symbol classes, one per byte.
@@ -265,7 +273,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) encode_kernel(EncArgs a) {
 #pragma unroll 1
             for (int g = 0; g < R / kGroup; g++) {
                 const bool want = active && hi32 <= end32 && hi32 + kGroup - (mpos & ~(kGroup - 1)) <= R;
-                if (!__any_sync(FULL, want)) break;
+                // a round costs the same for one lane as for 32: rounds that only a few lanes want are put off until
+                // they fill up, unless one of those lanes is about to run dry (see encode2.cu)
+                const unsigned wm = __ballot_sync(FULL, want);
+                if (!wm) break;
+                if (__popc(wm) < kMinRefillLanes && !__any_sync(FULL, want && hi32 - pos32 < kNeedySymbols)) break;
                 if (want) {
                     const uint4 sy = fetch16<DT, CELLS>(a.in, org + (size_t)hi32, n_total, end32 - hi32, qs, s_thr,
                                                         s_cls, qlo, qscale);
