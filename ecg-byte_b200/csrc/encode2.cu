@@ -25,10 +25,12 @@
 //            the root.  Tokens leave through the queue as 16-byte stores, eight per flush.
 //   The end of a record is a sentinel class that matches nothing; record switches and bytes that are
 //   their own token (text input) are handled at the phase boundary, outside the hot loop.  A ring
-//   holds 64 symbols; a walk that runs further than that past its last terminal (flat-line tokens
-//   of 128-256 symbols) simply lets the refill overwrite its history, and if the token then ends
-//   before the oldest entry still in the ring, the walker REWINDS: the ring restarts at the new
-//   token start and those few symbols are read a second time (about four times per record).
+//   holds 64 symbols, of which at most ECGB_ENC_HIST (16) are history behind the cursor; a walk that
+//   runs further than that past its last terminal (flat-line tokens of 64-256 symbols) lets the refill
+//   overwrite its history, and if the token then ends before the oldest entry still in the ring, the
+//   walker REWINDS: the ring restarts at the new token start and those symbols are read a second time.
+//   Refill rounds that fewer than ECGB_ENC_MINLANES (20) lanes want are put off until they fill up,
+//   unless a lane is running dry (a round costs the same for one lane as for 32).
 // HBM traffic is the algorithmic minimum: samples once, tokens once.
 #include <algorithm>
 #include <cstdlib>

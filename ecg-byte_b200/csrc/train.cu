@@ -4,28 +4,28 @@
 // hash map, lib.rs:28-48) -> argmax (lib.rs:92-94) -> merge (single-threaded in-place
 // left-to-right replacement, lib.rs:10-26).
 //
-// Here, per step, ONE streaming pass over the token stream (2-byte ids, read once,
-// written once -- the algorithmic 2*(n_t + n_{t+1}) bytes of SURVEY.md 8d):
-//   * merge_pass: tiles of 4096 tokens, decoupled look-back for the output offsets; every
-//     merge site also patches the pair histogram for the windows it destroys/creates
-//     (block-private shared-memory table, flushed once per CTA into an open-addressing hash
-//     table in global memory/L2), so the histogram always equals a full recount and no
-//     second pass over the tokens is needed;
-//   * argmax with the deterministic tie rule (max count, then smallest (left,right)) over a
-//     candidate list (every slot whose count is >= tau), falling back to a table scan that
-//     lowers tau when the list runs dry.
-// One device: train_loop_kernel runs every step inside ONE persistent cooperative kernel; once
-// the stream fits in the CTAs' shared memory it stays there (resident tail: each CTA owns a
-// chunk and treats the other CTAs exactly like the ranks of a sharded run).
-// (x,x) pairs: merge() is greedy left to right, so inside a run of x only the elements
-// at even run offsets start a site (lib.rs:14-18).  A tile finds the offset of its first
-// element by scanning backwards to the start of the run that enters it.
+// Here, per step, ONE streaming pass over the token stream (2-byte ids, read once, written once -- the algorithmic
+// 2*(n_t + n_{t+1}) bytes of SURVEY.md 8d):
+//   * merge_pass: tiles of 4096 tokens; every merge site also patches the pair histogram for the windows it
+//     destroys/creates (block-private shared-memory table, flushed once per CTA into an open-addressing hash table in
+//     global memory/L2), so the histogram always equals a full recount and no second pass over the tokens is needed;
+//   * argmax with the deterministic tie rule (max count, then smallest (left,right)) over a candidate list (every slot
+//     whose count is >= tau), falling back to a table scan that lowers tau when the list runs dry.
+// One device: train_loop_kernel runs every step inside ONE persistent cooperative kernel.  The stream is cut into one
+// contiguous CHUNK per CTA before the first step (ChunkWhere / chunk_step_begin); a chunk is merged in place -- in the
+// first token buffer while it is longer than 12 288 tokens, in the CTA's shared memory afterwards -- and a CTA treats the
+// other CTAs exactly like the ranks of a sharded run: all it needs from them is their 64-byte boundary record.  (The
+// round-1 scheme -- one stream, ping-pong buffers, decoupled look-back over tile tickets -- remains for the step-wise
+// merge_kernel and behind ECGB_RESIDENT_TAIL=1.)
+// (x,x) pairs: merge() is greedy left to right, so inside a run of x only the elements at even run offsets start a
+// site (lib.rs:14-18); the run position is carried from tile to tile and from chunk to chunk (run parity in the records).
 //
-// Sharded corpora (one trainer per rank): the same kernel takes a 2-token
-// left halo, a 3-token right halo and the parity of the x-run entering the shard; the
-// histogram patches go to a small delta table that is compacted into a list, exchanged
-// with the other ranks (all-gather, by the host) and applied by every rank, so every
-// rank holds the same global histogram and takes the same argmax without a reduction.
+// Sharded corpora (one trainer per rank = GPU): dist_loop_kernel is the same persistent loop on every rank;
+// the chain of chunks continues into the neighbouring ranks through one shard record per peer, every rank keeps a copy
+// of the GLOBAL histogram and takes the same argmax, and the ranks exchange histogram patches and shard records by
+// writing self-validating 8-byte units straight into each other's memory over NVLink (PeerView; no collective, no host,
+// no fence inside the loop).  The step-wise ecgb_trainer_dist_* calls (launches + two host-enqueued all-gathers per
+// step) remain as the NCCL reference path and provide the initial records / get_stats exchange.
 #include <cooperative_groups.h>
 
 #include <algorithm>
