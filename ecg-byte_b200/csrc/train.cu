@@ -1493,9 +1493,11 @@ __device__ __forceinline__ void dist_loop_body(const TrainView &v, const PeerVie
         {
             const int n_peers = pv.world - 1;
             const int per_peer = max(1, min(kApplyCtas, (int)gridDim.x / max(n_peers, 1)));
-            const int slot = (int)blockIdx.x / per_peer, sub = (int)blockIdx.x % per_peer;  // which peer, which share of its list
-            if (slot < n_peers) {
+            const int groups = max(1, (int)gridDim.x / per_peer);  // groups of per_peer CTAs; a group may serve several peers
+            const int group = (int)blockIdx.x / per_peer, sub = (int)blockIdx.x % per_peer;
+            for (int slot = group; group < groups && slot < n_peers; slot += groups) {
                 const int r = slot < pv.rank ? slot : slot + 1;
+                __syncthreads();  // peer_cnt[0] of the previous peer has been read
                 if (threadIdx.x == 0)
                     sm.peer_cnt[0] = min(wait_unit(mine + peer_flag_off(pv.world, par, r), peer_tag(pv.epoch, step), abort, pv.timeout_ns,
                                                    (2u << 28) | ((uint32_t)r << 20) | (step & 0xFFFFFu)), pv.cap);

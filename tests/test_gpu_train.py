@@ -195,6 +195,7 @@ def test_persistent_sharded_loop_one_gpu_many_ranks(oracle, small_corpus):
     text = rng.integers(97, 100, size=5000).astype(np.uint8)
     _check_persistent(oracle, text, [1700, 3300], 60)
     _check_persistent(oracle, text, [0, 1, 2, 4999], 40, max_ctas=8)   # empty and single-token shards
+    _check_persistent(oracle, text, [1000, 2000, 3000, 4000], 30, max_ctas=2)   # fewer CTAs than peers: a CTA applies several lists
     runs = np.concatenate([np.full(4100, 105, np.uint8), rng.integers(104, 107, size=50).astype(np.uint8),
                            np.full(8300, 105, np.uint8), np.array([106, 105, 105], np.uint8)])
     for cuts in ([4096], [4097, 4150], [100, 4200, 12000], [6000, 6001, 6002]):
