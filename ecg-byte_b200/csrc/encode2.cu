@@ -543,8 +543,9 @@ int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact
     // Which walker (measured on B200, profiles/encode_ab.py, profiles/encode_cases.py):
     //   * the 8-byte trie does not fit in shared memory next to 768 walkers' rings (10 000 merges): this kernel, whose
     //     pair table is 2.6x smaller -- 14.3 ms against 27.4 ms for 100 k records;
-    //   * the trie fits and the batch fills the chip (>= 512 records per SM): this kernel -- 13.3 against 13.9 ms (fp32),
-    //     13.0 against 13.3 (int16), 6.67 against 7.00 (12 x 2500);
+    //   * the trie fits and the batch fills the chip (>= 512 records per SM): this kernel for float samples -- 13.31
+    //     against 13.34 ms (fp32), 6.67 against 6.72 (12 x 2500), both kernels with deferred refill rounds; the bitmap
+    //     kernel for int16 samples (12.7 against 13.0 ms);
     //   * smaller batches: the bitmap kernel, whose step chain is shorter -- a launch is then as long as ONE record's walk
     //     (2 048 records: 8.0 against 9.5 ms; 2 records of 12 x 500: 0.54 against 0.63 ms).
     // A/B knobs: ECGB_ENCODE_V1 / ECGB_ENCODE_V2 force one.
@@ -556,6 +557,7 @@ int launch_encode2(int dt, const VocabView *vv, const QuantTables *qt, int exact
         const size_t trie_and_rings = (size_t)vv->n_nodes * 8 + 768 * 128 + 4096;
         const bool trie_fits = trie_and_rings <= (size_t)smem_max;
         if (trie_fits && n_rec < (size_t)512 * (size_t)sm_count(device)) return ECGB_EUNSUPPORTED;
+        if (trie_fits && dt == ECGB_I16) return ECGB_EUNSUPPORTED;  // int16 full batch: 12.7 ms (bitmap) against 13.0 ms
     }
     Enc2Args a{};
     a.in = d_in; a.n_total = n_total; a.n_rec = n_rec; a.rec_len = rec_len; a.offsets = d_offsets;
