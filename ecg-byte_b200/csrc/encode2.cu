@@ -443,13 +443,15 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
                     const uint32_t x1 = (cw & himask) | sm_code;
                     const uint32_t addr1 = A + x1;
                     const uint32_t e1 = lds32(addr1);
-                    uint32_t ref = 0;
-                    int32_t nq = 0;
-                    bool got = true;
-                    if (((e1 ^ x1) & kCheck) == 0u) { ref = addr1; nq = q + 2; }
-                    else if (m & 2u) { ref = m >> 8; nq = mq + 4; }
-                    else if (m & 1u) { ref = (m >> 8) - (m & lomask) + sm_code; nq = mq + 2; }
-                    else got = false;  // sentinel at the root: end of record, or a byte that is its own token
+                    // which slot holds the token and where the next one starts, without branches (the four cases would
+                    // otherwise run one after the other inside this already thinly populated block): the single probe
+                    // hit, else the pair that set m ended on a terminal, else only its first symbol did
+                    const bool hit1 = ((e1 ^ x1) & kCheck) == 0u;
+                    const bool m2 = (m & 2u) != 0u;
+                    const uint32_t ref_m = (m >> 8) - (m2 ? 0u : (m & lomask) - sm_code);
+                    const uint32_t ref = hit1 ? addr1 : ref_m;
+                    const int32_t nq = hit1 ? q + 2 : mq + (m2 ? 4 : 2);
+                    const bool got = hit1 || (m & 3u) != 0u;  // else: sentinel at the root -- end of record, or a byte that is its own token
                     if (got) {
                         sts16(queue_at(queue_lane, cnt), tok_of(ref));
                         cnt++;
