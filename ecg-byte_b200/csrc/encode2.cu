@@ -452,26 +452,24 @@ __global__ void __launch_bounds__(kThreads2, 1) encode2_kernel(Enc2Args a) {
                     const uint32_t ref = hit1 ? addr1 : ref_m;
                     const int32_t nq = hit1 ? q + 2 : mq + (m2 ? 4 : 2);
                     const bool got = hit1 || (m & 3u) != 0u;  // else: sentinel at the root -- end of record, or a byte that is its own token
-                    if (got) {
-                        sts16(queue_at(queue_lane, cnt), tok_of(ref));
-                        cnt++;
-                        q = mq = nq;
-                        m = 0;
-                        A = rootA;
-                        if ((nq >> 1) + 1 < hi32 - kRing2) {  // the restart point has left the ring
-                            parked = rewind = true;
-                            walk = false;
+                    // the rest without branches too: lanes that got a token queue it and restart at the root; a lane whose
+                    // restart point has left the ring (left) or that got nothing parks until the phase boundary
+                    const bool left = got && ((nq >> 1) + 1 < hi32 - kRing2);
+                    const uint32_t tok = tok_of(got ? ref : tab_sa);
+                    if (got) sts16(queue_at(queue_lane, cnt), tok);
+                    cnt += got ? 1u : 0u;
+                    q = got ? nq : q;
+                    mq = got ? nq : mq;
+                    m = got ? 0u : m;
+                    A = got ? rootA : A;
+                    parked = parked || !got || left;
+                    rewind = rewind || left;
+                    walk = got && !left;
 #ifdef ECGB_ENC_STATS
-                            if ((blockIdx.x & 7u) == 0 && threadIdx.x < 32) atomicAdd(&g_enc_stats[50], 1ull);
+                    if (left && (blockIdx.x & 7u) == 0 && threadIdx.x < 32) atomicAdd(&g_enc_stats[50], 1ull);
 #endif
-                        } else {
-                            ra = ring_at2(ring_lane, q + 2);
-                            cw = lds16(ra);
-                        }
-                    } else {
-                        parked = true;
-                        walk = false;
-                    }
+                    ra = ring_at2(ring_lane, q + 2);  // harmless for a parked lane: any ring address is a valid one
+                    cw = lds16(ra);
                 }
             }
         }
